@@ -1,0 +1,114 @@
+/*
+ * vllmini_b200 -- C ABI of the B200-native paged-attention decode path.
+ *
+ * This is the drop-in boundary for the ONE hot path of MDK8888/vllmini that this
+ * project replaces: the two native entry points its Python host calls,
+ *
+ *     paged_attention_cuda.paged_attention_v1            (vllmini/model/gpt2.py:94)
+ *     paged_attention_cuda.cache_ops.reshape_and_cache   (vllmini/model/gpt2.py:81)
+ *
+ * which the reference implements as a torch/pybind11 extension
+ * (paged_attention_ext/paged_attention_cuda/paged_attention_cuda.cpp:7-25, :56-59;
+ *  cache_kernels.h:11-14).  Here the same two operations are exported from a plain
+ * shared library (libvllmini_b200.so): extern "C", raw device pointers, sizes and
+ * strides in ELEMENTS, a CUDA stream handle passed as void*.  No torch types, no
+ * exceptions, no allocation, no synchronisation: every call only enqueues work on
+ * `stream` and returns.  The Python shim that reproduces the reference's positional
+ * signatures on top of this ABI is vllmini_b200/dropin/paged_attention_cuda/.
+ *
+ * Return value: 0 on success, a negative VB200_ERR_* code otherwise;
+ * vb200_last_error() returns a thread-local human-readable message for the last
+ * failing call on the calling thread.
+ *
+ * Data layout (owned by the caller, vllmini/kv_cache.py:13-14):
+ *   key_cache   [num_blocks, num_kv_heads, head_size/8, block_size, 8]  fp16
+ *   value_cache [num_blocks, num_kv_heads, head_size,   block_size]     fp16
+ *   block_tables [num_seqs, max_num_blocks_per_seq] int32, seq_lens [num_seqs] int32
+ *   slot_mapping [num_tokens] int64 (negative = padding, skipped)
+ */
+#ifndef VLLMINI_B200_H_
+#define VLLMINI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_ABI_VERSION 1
+
+enum {
+  VB200_OK = 0,
+  VB200_ERR_CUDA = -1,              /* a CUDA runtime call failed (message has the cudaError string) */
+  VB200_ERR_BLOCK_SIZE = -2,        /* reference: TORCH_CHECK "Unsupported block size" (attention_kernels.cu:800-802) */
+  VB200_ERR_HEAD_SIZE = -3,         /* reference: TORCH_CHECK "Unsupported head size" (attention_kernels.cu:763-765) */
+  VB200_ERR_INVALID_ARGUMENT = -4,  /* null pointer, negative size, misaligned pointer/stride */
+  VB200_ERR_UNSUPPORTED = -5        /* a feature of the reference signature this build does not implement */
+};
+
+/*
+ * paged_attention_v1, fp16 query/cache ("auto" kv-cache dtype), no ALiBi, no block-sparsity:
+ * the one arm of the reference dispatch vllmini reaches.
+ * Replaces: paged_attention_v1(...) host entry, attention_kernels.cu:805-826, its launcher
+ * :693-767 and kernel :86-527.
+ *
+ *   out        [num_seqs, num_heads, head_size] fp16, contiguous (written)
+ *   query      [num_seqs, num_heads, head_size] fp16, row stride q_stride elements
+ *   kv_block_stride = key_cache.stride(0), kv_head_stride = key_cache.stride(1); the same two
+ *                strides address value_cache (reference: attention_kernels.cu:402-403)
+ *   scale      softmax scale (head_size ** -0.5 in vllmini, gpt2.py:13)
+ *   max_seq_len upper bound on seq_lens[] (vllmini passes capacity, scheduler.py:97); used only
+ *                to pick the split-KV factor
+ *   workspace  optional device scratch for split-KV partials; may be NULL (=> no split).
+ *                Must be zero-filled once before its first use; the kernel leaves it reusable.
+ *                Size from vb200_paged_attention_v1_workspace_bytes().
+ *   device     CUDA device ordinal the pointers live on (reference: OptionalCUDAGuard, :736)
+ *   stream     cudaStream_t (reference: at::cuda::getCurrentCUDAStream(), :737)
+ *
+ * seq_lens[s] == 0 yields zeros for that row, as in the reference.  Entries of block_tables
+ * at or beyond ceil(seq_len/block_size) are never read (attention_kernels.cu:227).
+ */
+int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache, const void* value_cache,
+                                 const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
+                                 int32_t num_heads, int32_t num_kv_heads, int32_t head_size, int32_t block_size,
+                                 int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
+                                 int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
+                                 size_t workspace_bytes, int32_t device, void* stream);
+
+/* Bytes of split-KV workspace that lets the launcher use its preferred split factor for this
+ * problem shape (0 when it would not split). */
+size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
+                                                int32_t block_size, int32_t max_seq_len);
+
+/*
+ * reshape_and_cache, fp16 ("auto"): scatter new K/V rows into the paged caches by slot.
+ * Replaces: reshape_and_cache(...) host entry cache_kernels.cu:256-281 and kernel :152-207.
+ *
+ *   key, value [num_tokens, num_heads, head_size] fp16, row strides key_stride / value_stride
+ *   x          key_cache.size(4) (8 for fp16)
+ * Bit-exact copy.  slot_mapping[t] < 0 skips token t (cache_kernels.cu:166-169).
+ */
+int vb200_reshape_and_cache_f16(const void* key, const void* value, void* key_cache, void* value_cache,
+                                const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                                int32_t head_size, int32_t block_size, int32_t x, int64_t key_stride,
+                                int64_t value_stride, int32_t device, void* stream);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* vb200_last_error(void);
+
+/* VB200_ABI_VERSION the library was built with. */
+int32_t vb200_abi_version(void);
+
+/* Number of kernel launches this library has enqueued since load (all threads); used by
+ * bench.py to report gpu_launches and by tests to prove the CUDA path ran. */
+uint64_t vb200_launch_count(void);
+
+/* Tuning override for benchmarking/ablation (not needed by callers): forces the split-KV factor
+ * (0 = heuristic) and pipeline variant (0 = default).  Returns the previous packed value. */
+int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLLMINI_B200_H_ */

@@ -1,0 +1,119 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, rejects bad arguments with the documented codes (paths that return before any CUDA
+call), and the Python shim mirrors the reference's surface and error behaviour."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT
+
+import vllmini_b200
+from vllmini_b200 import _native, ops
+
+HEADER = os.path.join(ROOT, "include", "vllmini_b200.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    assert os.path.isfile(_native.LIB_PATH), "build with `python -m vllmini_b200.build`"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    names = header_functions()
+    assert {"vb200_paged_attention_v1_f16", "vb200_reshape_and_cache_f16", "vb200_last_error"} <= set(names)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vllmini_b200.h but not exported"
+    assert set(names) == set(_native.SYMBOLS), "ctypes table and header disagree"
+
+
+def test_abi_version_and_counters():
+    lib = _native.load()
+    assert lib.vb200_abi_version() == _native.ABI_VERSION == 1
+    assert _native.launch_count() >= 0
+    prev = _native.set_tuning(0, 0)
+    assert isinstance(prev, int)
+
+
+def test_library_has_sm100a_code_and_blackwell_instructions():
+    """The hot kernel must be real sm_100a code: bulk async copies (UBLKCP), mbarrier transactions
+    (SYNCS) and the mixed-precision FHFMA -- checked in the SASS of the built library."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5vb20012pa_v1_kernelILi64ELi16ELi4ELi2EEEvNS_8PaParamsE",
+                           _native.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "FHFMA", "CREDUX.MAX.F32", "LDS.128"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_c_abi_argument_validation_without_gpu():
+    lib = _native.load()
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    def attn(**kw):
+        a = dict(num_seqs=1, num_heads=12, num_kv_heads=12, head_size=64, block_size=16, mb=4, msl=64,
+                 qs=768, kbs=12 * 64 * 16, khs=64 * 16)
+        a.update(kw)
+        return lib.vb200_paged_attention_v1_f16(one, one, one, one, one, one, a["num_seqs"], a["num_heads"],
+                                                a["num_kv_heads"], a["head_size"], a["block_size"], a["mb"], a["msl"],
+                                                a["qs"], a["kbs"], a["khs"], 0.125, None, 0, 0, None)
+    assert attn(block_size=4) == -2 and "Unsupported block size: 4" in _native.last_error()
+    assert attn(block_size=64) == -2
+    assert attn(head_size=80) == -3 and "Unsupported head size: 80" in _native.last_error()
+    assert attn(num_heads=12, num_kv_heads=5) == -4
+    assert attn(qs=770) == -4 and "stride" in _native.last_error()
+    assert attn(num_seqs=0) == 0                       # empty batch is a no-op
+    assert attn(num_seqs=-1) == -4
+    assert lib.vb200_reshape_and_cache_f16(one, one, one, one, one, 0, 12, 64, 16, 8, 768, 768, 0, None) == 0
+    assert lib.vb200_reshape_and_cache_f16(one, one, one, one, one, 1, 12, 64, 16, 7, 768, 768, 0, None) == -4
+    assert lib.vb200_reshape_and_cache_f16(None, one, one, one, one, 1, 12, 64, 16, 8, 768, 768, 0, None) == -4
+    assert lib.vb200_paged_attention_v1_workspace_bytes(256, 12, 64, 16, 1024) == 0      # big batch: no split
+    assert lib.vb200_paged_attention_v1_workspace_bytes(1, 12, 64, 16, 8192) > 0         # tiny batch: split-KV
+
+
+def test_dropin_surface_matches_reference_package():
+    vllmini_b200.install_dropin()
+    sys.modules.pop("paged_attention_cuda", None)
+    import paged_attention_cuda as pac
+    assert pac.__all__ == ["paged_attention_v1", "paged_attention_v2", "cache_ops"]   # reference __init__.py:4-8
+    for name in ("swap_blocks", "copy_blocks", "reshape_and_cache", "reshape_and_cache_flash", "convert_fp8"):
+        assert callable(getattr(pac.cache_ops, name))                                  # paged_attention_cuda.cpp:57-61
+    from paged_attention_cuda import paged_attention_v1, cache_ops                     # gpt2.py:5
+    assert paged_attention_v1 is ops.paged_attention_v1 and cache_ops.reshape_and_cache is ops.reshape_and_cache
+
+
+def test_shim_error_behaviour_mirrors_reference():
+    h = torch.float16
+    q = torch.zeros(1, 12, 64, dtype=h)
+    kc = torch.zeros(4, 12, 8, 16, 8, dtype=h)
+    vc = torch.zeros(4, 12, 64, 16, dtype=h)
+    bt = torch.zeros(1, 4, dtype=torch.int32)
+    sl = torch.ones(1, dtype=torch.int32)
+    tail = [None, "auto", 1.0, 0, 0, 1, 1, 0]
+    # CPU tensors: the reference's device guard raises RuntimeError before anything else
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.paged_attention_v1(torch.empty_like(q), q, kc, vc, 12, 0.125, bt, sl, 16, 64, *tail)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.reshape_and_cache(q, q, kc, vc, torch.zeros(1, dtype=torch.int64), "auto", 1.0)
+    # uncalled exports exist but are explicit about being out of scope
+    with pytest.raises(NotImplementedError):
+        ops.paged_attention_v2()
+    with pytest.raises(NotImplementedError):
+        ops.swap_blocks(q, q, bt)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _native.load()

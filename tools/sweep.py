@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Kernel-only timing sweep over pipeline variants / split factors (development tool, GPU box).
+
+    python tools/sweep.py [--configs M,C1,...] [--out gpurun_out/sweep.json]
+
+Prints achieved algorithmic GB/s per (config, variant, splits).  Inputs exceed L2 (pool >= 1 GiB
+or the workload itself), CUDA-event timing over back-to-back launches rotating distinct pools.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vllmini_b200 import _native, ops  # noqa: E402
+
+CONFIGS = {
+    # name: (S, H, D, B, ctx)
+    "M": (256, 12, 64, 16, 1024),
+    "C1": (64, 12, 64, 16, 512),
+    "L8k": (256, 20, 64, 16, 8192),
+    "L4k_b8": (256, 20, 64, 8, 4096),
+    "L4k_b32": (256, 20, 64, 32, 4096),
+    "S1_8k": (1, 12, 64, 16, 8192),
+    "S8_2k": (8, 12, 64, 16, 2048),
+}
+
+
+def algorithmic_bytes(S, H, D, B, lens):
+    kv = sum(2 * int(l) * H * D * 2 for l in lens)
+    return kv + 2 * S * H * D * 2 + sum(((int(l) + B - 1) // B) * 4 for l in lens) + S * 4
+
+
+def make(S, H, D, B, ctx, seed, dev, mixed=False):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    if mixed:
+        lens = torch.randint(128, 2049, (S,), generator=g, device=dev, dtype=torch.int32)
+    else:
+        lens = torch.full((S,), ctx, dtype=torch.int32, device=dev)
+    nblk = (int(lens.max()) + B - 1) // B
+    NB = S * nblk
+    kc = torch.randn(NB, H, D // 8, B, 8, generator=g, device=dev, dtype=torch.float16)
+    vc = torch.randn(NB, H, D, B, generator=g, device=dev, dtype=torch.float16)
+    q = torch.randn(S, H, D, generator=g, device=dev, dtype=torch.float16)
+    bt = torch.randperm(NB, generator=g, device=dev).to(torch.int32).view(S, nblk)
+    return q, kc, vc, bt, lens
+
+
+def time_config(name, variant, splits, iters=20, warm=5, ref=None):
+    S, H, D, B, ctx = CONFIGS[name]
+    dev = torch.device("cuda:0")
+    bytes_one = 2 * S * ctx * H * D * 2
+    npools = max(2, min(6, int((1 << 30) // max(bytes_one, 1)) + 1)) if bytes_one < (1 << 30) else 2
+    pools = [make(S, H, D, B, ctx, s, dev) for s in range(npools)]
+    outs = [torch.empty_like(p[0]) for p in pools]
+    _native.set_tuning(splits, variant)
+    def call(i):
+        q, kc, vc, bt, sl = pools[i % npools]
+        if ref is None:
+            ops.paged_attention_v1(outs[i % npools], q, kc, vc, H, D ** -0.5, bt, sl, B, ctx, None, "auto", 1.0, 0, 0, 1, 1, 0)
+        else:
+            ref.paged_attention_v1(outs[i % npools], q, kc, vc, H, D ** -0.5, bt, sl, B, ctx, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    for i in range(warm):
+        call(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i in range(iters):
+        evs[i][0].record()
+        call(i)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+    med = ts[len(ts) // 2]
+    ab = algorithmic_bytes(S, H, D, B, [ctx] * S)
+    _native.set_tuning(0, 0)
+    del pools, outs
+    torch.cuda.empty_cache()
+    return dict(config=name, variant=variant, splits=splits, us_median=med, us_min=ts[0], gbps=ab / med / 1e3,
+                bytes=ab, impl="ref" if ref is not None else "new")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="M,C1")
+    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--splits", default="0")
+    ap.add_argument("--ref", action="store_true", help="also time the reference's own kernel (oracle/_ref)")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
+    a = ap.parse_args()
+    res = []
+    ref = None
+    if a.ref:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import load_ref_extension
+        ref = load_ref_extension()
+    for name in a.configs.split(","):
+        for v in [int(x) for x in a.variants.split(",")]:
+            for sp in [int(x) for x in a.splits.split(",")]:
+                r = time_config(name, v, sp)
+                res.append(r)
+                print(json.dumps(r), flush=True)
+        if ref is not None:
+            r = time_config(name, 0, 0, ref=ref)
+            res.append(r)
+            print(json.dumps(r), flush=True)
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    with open(a.out, "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""ctypes binding of libvllmini_b200.so (the C ABI declared in include/vllmini_b200.h).
+
+There is deliberately NO fallback: if the library is missing or does not export every symbol of
+the header, importing the ops raises.  A GPU box without the built .so must fail loudly rather
+than silently run something else.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libvllmini_b200.so")
+
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/vllmini_b200.h one to one
+_vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+SYMBOLS = {
+    "vb200_paged_attention_v1_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                            _i64, _i64, _i64, _f32, _vp, _sz, _i32, _vp]),
+    "vb200_paged_attention_v1_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "vb200_reshape_and_cache_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
+                                           _i32, _vp]),
+    "vb200_last_error": (ctypes.c_char_p, []),
+    "vb200_abi_version": (_i32, []),
+    "vb200_launch_count": (ctypes.c_uint64, []),
+    "vb200_set_tuning": (_i32, [_i32, _i32]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raise RuntimeError with a build hint if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"vllmini_b200: native library not found at {LIB_PATH}. Build it with "
+            "`python -m vllmini_b200.build` (nvcc, sm_100a). There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise RuntimeError(f"vllmini_b200: {LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = lib.vb200_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"vllmini_b200: ABI version mismatch: library {got}, binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().vb200_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def launch_count() -> int:
+    return int(load().vb200_launch_count())
+
+
+def set_tuning(force_num_splits: int = 0, variant: int = 0) -> int:
+    return int(load().vb200_set_tuning(int(force_num_splits), int(variant)))

@@ -1,0 +1,66 @@
+"""Build libvllmini_b200.so (the C-ABI library) in-tree with nvcc for sm_100a.
+
+    python -m vllmini_b200.build [--force] [--verbose]
+
+The .so lands in vllmini_b200/lib/ (git-ignored, but shipped to the GPU box by gpurun).
+nvcc cross-compiles without a GPU.  No torch involvement: the library only needs the CUDA
+runtime (linked statically), so it can be bound from any host language.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libvllmini_b200.so")
+SOURCES = ["abi.cu", "cache_kernels.cu", "paged_attention.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "vllmini_b200.h")]
+
+
+def _nvcc() -> str:
+    home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cand = os.path.join(home, "bin", "nvcc")
+    return cand if os.path.isfile(cand) else "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [
+        _nvcc(), "-shared", "-o", LIB_PATH + ".tmp",
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-lineinfo", "-std=c++17",
+        "-Xcompiler", "-fPIC,-O3,-Wall",
+        "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+        "-t", "0",
+    ]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))
+    sys.exit(0)

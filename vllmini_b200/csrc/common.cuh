@@ -1,0 +1,160 @@
+// Shared device helpers (sm_100a PTX wrappers) and host-side error plumbing for libvllmini_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "vllmini_b200.h"
+
+namespace vb200 {
+
+// ------------------------------------------------------------------------------------------
+// host: error state, device guard, launch counter
+// ------------------------------------------------------------------------------------------
+char* error_buffer();              // thread-local, 512 bytes (abi.cu)
+void count_launch();               // atomic ++ of the library-wide launch counter (abi.cu)
+int device_sm_count();             // SMs of the current device (cached; 148 if it cannot be queried)
+
+inline int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define VB200_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::vb200::set_error(VB200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// Equivalent of the reference's at::cuda::OptionalCUDAGuard (attention_kernels.cu:736,
+// cache_kernels.cu:276): make `device` current for the launch, restore on scope exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && device >= 0 && device != prev) {
+      status = cudaSetDevice(device);
+      switched = (status == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// device: PTX wrappers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier (shared::cta) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  // make the initialised barriers visible to the async (TMA) proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "VB200_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra VB200_DONE;\n"
+      "bra VB200_WAIT;\n"
+      "VB200_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- 1-D bulk async copy global -> shared, completion on an mbarrier (SASS: UBLKCP) ----
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---- vector loads / stores ----
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+
+// ---- mixed-precision FMA: d = lo/hi(a) * lo/hi(b) + c, fp16 x fp16 exact, fp32 accumulate.
+//      PTX fma.rn.f32.f16 (sm_100+); SASS FHFMA with free .H0/.H1 operand selects. ----
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n"
+      ".reg .b16 al, ah, bl, bh;\n"
+      "mov.b32 {al, ah}, %1;\n"
+      "mov.b32 {bl, bh}, %2;\n"
+      "fma.rn.f32.f16 %0, al, bl, %3;\n"
+      "}\n"
+      : "=f"(d)
+      : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
+  float d;
+  asm("{\n"
+      ".reg .b16 al, ah, bl, bh;\n"
+      "mov.b32 {al, ah}, %1;\n"
+      "mov.b32 {bl, bh}, %2;\n"
+      "fma.rn.f32.f16 %0, ah, bh, %3;\n"
+      "}\n"
+      : "=f"(d)
+      : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+
+// ---- warp-wide fp32 max in one instruction (redux.sync.max.f32, sm_100a; SASS CREDUX.MAX.F32) ----
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace vb200

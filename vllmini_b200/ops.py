@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference's operator interface for the paged-attention decode path.
+
+Same names, positional argument order, in-place semantics and error behaviour as the reference's
+pybind11 module `paged_attention_cuda` (paged_attention_ext/paged_attention_cuda/
+paged_attention_cuda.cpp:7-25 and :51-61, cache_kernels.h:5-22), implemented as a thin layer over
+the C ABI in include/vllmini_b200.h: this file only extracts pointers, sizes, strides and the
+current CUDA stream from torch tensors.  PyTorch is plumbing here (device memory + streams).
+
+Like the reference, every call is asynchronous on torch's current stream of the tensors' device,
+allocates nothing the caller can see, and returns None.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _native
+
+_ERR_NAMES = {-1: "CUDA error", -2: "Unsupported block size", -3: "Unsupported head size",
+              -4: "invalid argument", -5: "unsupported"}
+
+# per-device split-KV scratch (zero-filled once; the kernel leaves it reusable)
+_workspaces: Dict[int, torch.Tensor] = {}
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        # reference: TORCH_CHECK -> c10::Error -> Python RuntimeError
+        raise RuntimeError(f"vllmini_b200: {_native.last_error() or _ERR_NAMES.get(rc, 'error')} (code {rc})")
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        # reference: "CUDAGuardImpl initialized with non-CUDA DeviceType: cpu" 
+        raise RuntimeError(f"vllmini_b200: {name} must be a CUDA tensor, got device {t.device}")
+
+
+def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+    if nbytes <= 0:
+        return None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _workspaces.get(idx)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[idx] = ws
+    return ws
+
+
+def paged_attention_v1(
+    out: torch.Tensor,
+    query: torch.Tensor,
+    key_cache: torch.Tensor,
+    value_cache: torch.Tensor,
+    num_kv_heads: int,
+    scale: float,
+    block_tables: torch.Tensor,
+    seq_lens: torch.Tensor,
+    block_size: int,
+    max_seq_len: int,
+    alibi_slopes: Optional[torch.Tensor],
+    kv_cache_dtype: str,
+    kv_scale: float,
+    tp_rank: int = 0,
+    blocksparse_local_blocks: int = 0,
+    blocksparse_vert_stride: int = 1,
+    blocksparse_block_size: int = 1,
+    blocksparse_head_sliding_step: int = 0,
+) -> None:
+    """Decode attention over the paged KV cache; writes `out` in place.
+
+    Reference: attention_kernels.cu:805-826 (entry), :693-767 (launcher).  Shapes:
+    out/query [num_seqs, num_heads, head_size] (query may have any row stride, out is written as
+    contiguous [num_seqs, num_heads, head_size] whatever its nominal rank -- the reference does not
+    check out's rank either, tests/kernels/paged_attention.py:114); key_cache
+    [NB, KVH, D/8, B, 8]; value_cache [NB, KVH, D, B]; block_tables int32 [S, MB]; seq_lens int32 [S].
+    """
+    _require_cuda(query, "query")
+    if query.dtype != torch.float16:
+        # reference dispatch also has float/bfloat16 arms (quant_utils.cuh:529-566); vllmini is
+        # fp16-only (kv_cache.py:13-14, scheduler.py:13) and so is this build
+        raise RuntimeError(f"vllmini_b200: unsupported input type of kv cache: {query.dtype}")
+    if kv_cache_dtype != "auto":
+        raise RuntimeError(f"vllmini_b200: Unsupported data type of kv cache: {kv_cache_dtype}")
+    if alibi_slopes is not None:
+        raise RuntimeError("vllmini_b200: alibi_slopes is not supported (vllmini passes None, gpt2.py:105)")
+    if blocksparse_vert_stride > 1:
+        raise RuntimeError("vllmini_b200: block-sparse attention is not supported "
+                           "(vllmini passes blocksparse_vert_stride=1, gpt2.py:110)")
+    for t, name in ((out, "out"), (key_cache, "key_cache"), (value_cache, "value_cache"),
+                    (block_tables, "block_tables"), (seq_lens, "seq_lens")):
+        _require_cuda(t, name)
+    if block_tables.dtype != torch.int32:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {block_tables.dtype} (block_tables)")
+    if seq_lens.dtype != torch.int32:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {seq_lens.dtype} (seq_lens)")
+    if key_cache.dtype != torch.float16 or value_cache.dtype != torch.float16 or out.dtype != torch.float16:
+        raise RuntimeError("vllmini_b200: out, key_cache and value_cache must be float16")
+    if query.dim() != 3 or query.stride(2) != 1 or query.stride(1) != query.size(2):
+        raise RuntimeError("vllmini_b200: query must be [num_seqs, num_heads, head_size] with contiguous heads")
+    if not out.is_contiguous() or not block_tables.is_contiguous() or not seq_lens.is_contiguous():
+        raise RuntimeError("vllmini_b200: out, block_tables and seq_lens must be contiguous")
+    num_seqs, num_heads, head_size = query.shape
+    if out.numel() != query.numel():
+        raise RuntimeError("vllmini_b200: out must have num_seqs*num_heads*head_size elements")
+    max_blocks = block_tables.size(1) if block_tables.dim() == 2 else 0
+    dev = query.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
+                                                            int(max_seq_len))
+    ws = _workspace(dev, ws_bytes)
+    rc = lib.vb200_paged_attention_v1_f16(
+        out.data_ptr(), query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
+        block_tables.data_ptr(), seq_lens.data_ptr(),
+        num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size), max_blocks, int(max_seq_len),
+        query.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
+        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+        dev_index, stream)
+    _check(rc)
+
+
+def reshape_and_cache(
+    key: torch.Tensor,
+    value: torch.Tensor,
+    key_cache: torch.Tensor,
+    value_cache: torch.Tensor,
+    slot_mapping: torch.Tensor,
+    kv_cache_dtype: str,
+    kv_scale: float,
+) -> None:
+    """Scatter key/value rows [T, H, D] into the paged caches at slot_mapping (int64), in place.
+    Reference: cache_kernels.cu:256-281 (entry), :152-207 (kernel)."""
+    _require_cuda(key, "key")
+    if kv_cache_dtype != "auto":
+        raise RuntimeError(f"vllmini_b200: Unsupported data type of kv cache: {kv_cache_dtype}")
+    if key.dtype != torch.float16:
+        raise RuntimeError(f"vllmini_b200: unsupported input type of kv cache: {key.dtype}")
+    for t, name in ((value, "value"), (key_cache, "key_cache"), (value_cache, "value_cache"),
+                    (slot_mapping, "slot_mapping")):
+        _require_cuda(t, name)
+    if slot_mapping.dtype != torch.int64:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Long but found {slot_mapping.dtype} (slot_mapping)")
+    if value.dtype != torch.float16 or key_cache.dtype != torch.float16 or value_cache.dtype != torch.float16:
+        raise RuntimeError("vllmini_b200: value, key_cache and value_cache must be float16")
+    if key.dim() != 3 or key.stride(2) != 1 or key.stride(1) != key.size(2) \
+            or value.stride(2) != 1 or value.stride(1) != value.size(2):
+        raise RuntimeError("vllmini_b200: key/value must be [num_tokens, num_heads, head_size] with contiguous heads")
+    if key_cache.dim() != 5 or not key_cache.is_contiguous() or not value_cache.is_contiguous():
+        raise RuntimeError("vllmini_b200: key_cache must be contiguous [NB, H, D/x, B, x]; value_cache [NB, H, D, B]")
+    if not slot_mapping.is_contiguous():
+        raise RuntimeError("vllmini_b200: slot_mapping must be contiguous")
+    num_tokens, num_heads, head_size = key.shape
+    block_size, x = key_cache.size(3), key_cache.size(4)
+    dev = key.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.vb200_reshape_and_cache_f16(
+        key.data_ptr(), value.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr(),
+        num_tokens, num_heads, head_size, block_size, x, key.stride(0), value.stride(0), dev_index, stream)
+    _check(rc)
+
+
+# ---- the rest of the reference's exported surface: present so `import` matches, but out of the
+#      hot path (no vllmini caller) ----
+def paged_attention_v2(*args, **kwargs) -> None:
+    raise NotImplementedError("paged_attention_v2 is exported by the reference (paged_attention_cuda.cpp:27-48) "
+                              "but never called by vllmini; paged_attention_v1 here already splits long contexts")
+
+
+def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: torch.Tensor) -> None:
+    raise NotImplementedError("cache_ops.swap_blocks (cache_kernels.cu:24-63) has no vllmini caller")
+
+
+def copy_blocks(key_caches: List[torch.Tensor], value_caches: List[torch.Tensor],
+                block_mapping: torch.Tensor) -> None:
+    raise NotImplementedError("cache_ops.copy_blocks (cache_kernels.cu:96-148) has no vllmini caller")
+
+
+def reshape_and_cache_flash(*args, **kwargs) -> None:
+    raise NotImplementedError("cache_ops.reshape_and_cache_flash (cache_kernels.cu:283-317) has no vllmini caller")
+
+
+def convert_fp8(*args, **kwargs) -> None:
+    raise NotImplementedError("cache_ops.convert_fp8 (cache_kernels.cu:334-392) is test-only and fp8 is disabled "
+                              "in the reference build (no ENABLE_FP8)")
