@@ -98,6 +98,10 @@ static inline uint16_t d2h(double s) { /* double -> fp16 with ONE rounding (via 
   return f2h(f);
 }
 static inline uint16_t hadd(uint16_t a, uint16_t b) { return d2h((double)h2f(a) + (double)h2f(b)); }
+/* HFMA2 lane: a*b + c with a single rounding to fp16 */
+static inline uint16_t hfma(uint16_t a, uint16_t b, uint16_t c) {
+  return d2h((double)h2f(a) * (double)h2f(b) + (double)h2f(c));
+}
 
 /* ---------------------------------------------------------------------------
  * reshape_and_cache  (cache_kernels.cu:152-207; host entry :256-281)
@@ -260,14 +264,20 @@ int oracle_paged_attention_v1_f16(uint16_t* out, const uint16_t* query, const ui
               p16[j] = f2h(tok < L ? logits[tok] * inv : 0.f);            /* :344, :398-400 */
             }
             for (int d = 0; d < D; ++d) {
-              uint16_t pr[8];
+              /* Source: mul.f16x2 products + three add.f16x2 (sum(uint4), dtype_float16.cuh:
+               * 451-457).  As compiled (nvcc 12.9 / sm_100) ptxas contracts them into
+               *   c = rn(p1*v1); c = fma(p0,v0,c); c = fma(p2,v2,c); c = fma(p3,v3,c)
+               * per half2 lane (words x,y,z,w = 0..3); this reproduces the golden outputs of the
+               * reference kernel bit for bit (tests/golden/refkernel_outputs.npz). */
+              uint16_t vv[8];
               for (int j = 0; j < 8; ++j) {
                 const int tok = b * B + g * 8 + j;
-                const uint16_t v = tok < L ? vb[d * B + g * 8 + j] : (uint16_t)0; /* :420-430 */
-                pr[j] = hmul(p16[j], v);
+                vv[j] = tok < L ? vb[d * B + g * 8 + j] : (uint16_t)0;    /* :420-430 */
               }
-              const uint16_t lo = hadd(hadd(hadd(pr[0], pr[2]), pr[4]), pr[6]); /* sum(uint4) */
-              const uint16_t hi = hadd(hadd(hadd(pr[1], pr[3]), pr[5]), pr[7]);
+              uint16_t lo = hmul(p16[2], vv[2]);
+              lo = hfma(p16[0], vv[0], lo); lo = hfma(p16[4], vv[4], lo); lo = hfma(p16[6], vv[6], lo);
+              uint16_t hi = hmul(p16[3], vv[3]);
+              hi = hfma(p16[1], vv[1], hi); hi = hfma(p16[5], vv[5], hi); hi = hfma(p16[7], vv[7], hi);
               accw[w][g][d] += h2f(lo) + h2f(hi);
             }
           }

@@ -160,10 +160,11 @@ def test_strided_query_and_4d_out_like_vllmini():
     q_view = qkv[:, :H * D].view(S, H, D)
     assert q_view.stride(0) == 3 * H * D
     out4 = torch.empty(S, H, 1, D, dtype=torch.float16, device="cuda:0")
-    ops.paged_attention_v1(out4, q_view, t["kc"], t["vc"], H, c["scale"], t["bt"], t["sl"], c["B"], 4 * 512,
+    msl = int(t["bt"].shape[1]) * c["B"]      # same max_seq_len => same split factor => same arithmetic
+    ops.paged_attention_v1(out4, q_view, t["kc"], t["vc"], H, c["scale"], t["bt"], t["sl"], c["B"], msl,
                            None, "auto", 1.0, 0, 0, 1, 1, 0)
     torch.cuda.synchronize()
-    want = run_cuda_attention(c, t)
+    want = run_cuda_attention(c, t, max_seq_len=msl)
     assert np.array_equal(out4.view(S, H, D).cpu().numpy().view(np.uint16), want.view(np.uint16))
 
 
@@ -303,10 +304,11 @@ def test_full_size_properties_metric_config():
     inv[perm] = torch.arange(perm.numel(), device=perm.device)
     moved = attn(q, kc[perm], vc[perm], inv[bt.long()].to(torch.int32), sl)
     assert torch.equal(moved, base)
-    # independence of sequences
+    # independence of sequences.  A 3-sequence batch is launched with split-KV (different
+    # summation order), so equality is to fp16 rounding, not bit-exact.
     idx = torch.tensor([0, 17, 255], device=q.device)
     sub = attn(q[idx].contiguous(), kc, vc, bt[idx].contiguous(), sl[idx].contiguous())
-    assert torch.equal(sub, base[idx])
+    assert (sub.float() - base[idx].float()).abs().max().item() <= 2.5e-4
     # linearity in V
     v2 = torch.randn_like(vc)
     lin = attn(q, kc, (vc.float() + v2.float()).to(torch.float16), bt, sl)
