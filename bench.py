@@ -364,10 +364,8 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    if world > 1:
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0]), float(t[1])
+    from vllmini_b200 import sharding
+    ms_total, e2e_s = sharding.reduce_max([ms_total, e2e_s], dev)      # the job is as slow as its slowest rank
 
     if rank == 0:
         ms_step = ms_total / args.steps

@@ -24,6 +24,13 @@ CONFIGS = {
     "L8k": (256, 20, 64, 16, 8192),
     "L4k_b8": (256, 20, 64, 8, 4096),
     "L4k_b32": (256, 20, 64, 32, 4096),
+    "L1k_h20": (256, 20, 64, 16, 1024),
+    "L1k_h20_b8": (256, 20, 64, 8, 1024),
+    "L1k_h20_b32": (256, 20, 64, 32, 1024),
+    "L8k_b8": (256, 20, 64, 8, 8192),
+    "L8k_b32": (256, 20, 64, 32, 8192),
+    "MIX": (256, 12, 64, 16, -2048),     # ctx ~ U[128, 2048] (BASELINE configs[2])
+    "D128": (256, 8, 128, 16, 1024),
     "S1_8k": (1, 12, 64, 16, 8192),
     "S8_2k": (8, 12, 64, 16, 2048),
 }
@@ -51,10 +58,12 @@ def make(S, H, D, B, ctx, seed, dev, mixed=False):
 
 def time_config(name, variant, splits, iters=20, warm=5, ref=None):
     S, H, D, B, ctx = CONFIGS[name]
+    mixed = ctx < 0
+    ctx = abs(ctx)
     dev = torch.device("cuda:0")
     bytes_one = 2 * S * ctx * H * D * 2
     npools = max(2, min(6, int((1 << 30) // max(bytes_one, 1)) + 1)) if bytes_one < (1 << 30) else 2
-    pools = [make(S, H, D, B, ctx, s, dev) for s in range(npools)]
+    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(npools)]
     outs = [torch.empty_like(p[0]) for p in pools]
     _native.set_tuning(splits, variant)
     def call(i):
@@ -74,7 +83,7 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None):
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
     med = ts[len(ts) // 2]
-    ab = algorithmic_bytes(S, H, D, B, [ctx] * S)
+    ab = sum(algorithmic_bytes(S, H, D, B, p[4].tolist()) for p in pools) / npools
     _native.set_tuning(0, 0)
     del pools, outs
     torch.cuda.empty_cache()
