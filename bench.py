@@ -298,6 +298,77 @@ class HostDrivenStep:
         return self.h_out
 
 
+def run_full_model(args, dev, world, rank):
+    """Whole GPT-2 small decode step (cuBLAS GEMMs + LayerNorm + GELU via torch, the two hot ops via
+    the binding) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
+    driver of SURVEY.md 8f rank 1), CUDA-graph replayed.  Reported as context next to the hot-path
+    `value`; at N>1 rank 0's weights are broadcast over NCCL first (the path's only collective)."""
+    import numpy as np
+    import torch
+    from vllmini_b200 import sharding
+    from vllmini_b200.decode import BatchedKVState, GPT2Decoder, GPT2Shape, synthetic_gpt2_state_dict
+
+    shape = GPT2Shape(n_positions=2048)                    # ctx > 1024 needs n_positions raised (SURVEY.md section 0)
+    model = GPT2Decoder(shape, dev)
+    t0 = time.perf_counter()
+    model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=0 if rank == 0 else 1000 + rank))
+    t_bcast = None
+    if world > 1:
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        model.broadcast_weights(src=0)
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - tb
+    MB = 72                                                 # capacity 1152 tokens per sequence
+    kv = BatchedKVState(LAYERS * S * MB, LAYERS, H, D, B, S, MB, dev)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    kv.key_cache.normal_(generator=g)
+    kv.value_cache.normal_(generator=g)
+    # adopt a synthetic 1023-token history per sequence: 64 permuted blocks per (layer, sequence)
+    nblk = CTX // B
+    perm = torch.randperm(LAYERS * S * MB, generator=g, device=dev).to(torch.int32).cpu().numpy()
+    kv.h_tables[:, :, :nblk] = perm[: LAYERS * S * nblk].reshape(LAYERS, S, nblk)
+    owned = set(int(b) for b in perm[: LAYERS * S * nblk])
+    kv.free_blocks = type(kv.free_blocks)(int(b) for b in perm[LAYERS * S * nblk:])
+    kv.h_lens[:] = CTX - 1
+    kv.active[:] = True
+    kv.d_tables.copy_(torch.from_numpy(kv.h_tables))
+    assert len(owned) == LAYERS * S * nblk
+    ids = torch.randint(0, shape.vocab_size, (S,), generator=g, device=dev)
+    kv.begin_decode_step()
+    model.capture_decode_graph(kv)
+    model.g_ids.copy_(ids)
+
+    def step():
+        kv.begin_decode_step()
+        model.g_pos.copy_(torch.from_numpy(kv.positions()), non_blocking=True)
+        nxt = model.replay_decode_graph()
+        model.g_ids.copy_(nxt)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = min(args.steps, 60)
+    t1 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t1
+    ms, wall = sharding.reduce_max([e0.elapsed_time(e1), wall], dev)
+    return {"value": world * S / (ms / steps * 1e-3), "unit": "tokens/s", "ms_per_step": ms / steps,
+            "wall_ms_per_step": wall / steps * 1e3, "steps": steps,
+            "model": "GPT-2 small (12 layers, 12x64 heads, vocab 50257), synthetic seeded weights, fp16",
+            "ctx": f"{CTX}..{CTX + steps + 4} (grows one token per step)",
+            "how": "vllmini_b200.decode: batched block bookkeeping on host (no D2H sync), whole step in one CUDA "
+                   "graph (torch/cuBLAS GEMMs + LayerNorm + GELU + the two hot-path kernels per layer + argmax)",
+            "weight_broadcast_s": t_bcast, "setup_s": time.perf_counter() - t0}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -367,6 +438,17 @@ def run_gpu_arm(args):
     from vllmini_b200 import sharding
     ms_total, e2e_s = sharding.reduce_max([ms_total, e2e_s], dev)      # the job is as slow as its slowest rank
 
+    full_model = None
+    h2d_bytes, d2h_bytes = hd.h2d, hd.d2h
+    if not args.no_full_model:
+        del hd
+        hp.key_cache = hp.value_cache = None
+        torch.cuda.empty_cache()
+        try:
+            full_model = run_full_model(args, dev, world, rank)
+        except Exception as e:
+            full_model = {"value": None, "error": repr(e)}
+
     if rank == 0:
         ms_step = ms_total / args.steps
         value = world * S / (ms_step * 1e-3)
@@ -381,11 +463,11 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * S, "seq_len": CTX,
                        "parallelism": f"request-sharded x{world} (no data-path collective)",
-                       "kv_pool_gb_per_gpu": round(2 * hp.key_cache.numel() * 2 / 1e9, 2),
+                       "kv_pool_gb_per_gpu": round(2 * LAYERS * S * (CTX // B) * H * D * B * 2 / 1e9, 2),
                        "l2_policy": "inputs larger than L2: each layer reads 805 MB of distinct KV blocks, "
                                     "9.66 GB per step, no flush needed",
                        "timing": "CUDA events on the launch stream, max over ranks"},
-            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": hd.h2d, "d2h_bytes_per_step": hd.d2h,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "how": "pinned host q/k/v+slots+block tables -> device, 24 launches, attention output -> "
                            "pinned host, per-layer pipelining on 3 streams, host sync every step"},
@@ -399,6 +481,8 @@ def run_gpu_arm(args):
                          "launches_timed": len(attn_us), "attention_share_of_step": attn_mean_us * LAYERS / (ms_step * 1e3),
                          "traffic": recorded_traffic()},
         }
+        if full_model is not None:
+            line["full_model"] = full_model
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_attention_sample()
@@ -418,6 +502,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vllmini_b200", choices=["vllmini_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-model", action="store_true", help="skip the whole-GPT-2 decode context row")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

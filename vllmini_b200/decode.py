@@ -1,0 +1,330 @@
+"""Batched decode driver for the paged-attention hot path.
+
+The reference steps ONE sequence per forward pass with dozens of GPU->CPU syncs in its block
+bookkeeping (vllmini/scheduler.py:55-108, block_manager.py:28-63, kv_cache.py:56-73), so its host code
+never exercises the kernels at batch > 1.  This module is the harness-side driver that does: it keeps
+the reference's data model -- one KV pool for all layers, FIFO free list, per-(sequence, layer) block
+tables padded with -1, int64 slot mappings, the cache layouts of kv_cache.py:13-14 -- but advances all
+sequences together, with the bookkeeping vectorised on the host (numpy) and no device->host sync on
+the step path.
+
+  BatchedKVState   batched counterpart of KVCache + BlockManager.decode_step
+  GPT2Decoder      a GPT-2 host model with the reference GPT2LMHeadModel's parameter names
+                   (state_dict-compatible with vllmini/model/gpt2.py:243-331): GEMMs / LayerNorm /
+                   GELU are torch (cuBLAS) calls -- plumbing -- and the two hot ops go through
+                   vllmini_b200.ops.  Optional CUDA-graph capture of the whole decode step.
+
+Nothing here is required to use the drop-in with an unmodified vllmini; it exists so that the
+BASELINE configs with 256+ concurrent sequences can be driven end to end.
+"""
+from __future__ import annotations
+
+import collections
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+@dataclass
+class GPT2Shape:
+    """GPT-2 small by default (transformers.GPT2Config() defaults)."""
+    n_layer: int = 12
+    n_head: int = 12
+    n_embd: int = 768
+    vocab_size: int = 50257
+    n_positions: int = 1024
+    layer_norm_epsilon: float = 1e-5
+
+    @property
+    def head_size(self) -> int:
+        return self.n_embd // self.n_head
+
+
+# ---------------------------------------------------------------------------------------------
+# KV bookkeeping
+# ---------------------------------------------------------------------------------------------
+class BatchedKVState:
+    """Paged KV pool + block tables for up to `max_seqs` concurrent sequences, all layers.
+
+    Layout contract is the reference's (kv_cache.py:13-14, 30-35): key_cache [NB, H, D/8, B, 8],
+    value_cache [NB, H, D, B]; one pool shared by all layers, a block belongs to one (sequence,
+    layer); table rows are int32 padded with -1; free list is FIFO (kv_cache.py:25-26, 60, 83).
+    Unlike the reference's allocate_for_prefill (one block per layer whatever the prompt length,
+    kv_cache.py:25 -- prompts longer than a block spill into the neighbour's block), prefill here
+    allocates ceil(prompt_len / B) blocks per layer.
+    """
+
+    def __init__(self, num_blocks: int, num_layers: int, num_heads: int, head_size: int, block_size: int,
+                 max_seqs: int, max_blocks_per_seq: int, device: torch.device, dtype=torch.float16):
+        assert head_size % 8 == 0
+        self.num_blocks, self.num_layers, self.num_heads = num_blocks, num_layers, num_heads
+        self.head_size, self.block_size = head_size, block_size
+        self.max_seqs, self.max_blocks_per_seq = max_seqs, max_blocks_per_seq
+        self.device = device
+        self.key_cache = torch.zeros(num_blocks, num_heads, head_size // 8, block_size, 8, dtype=dtype, device=device)
+        self.value_cache = torch.zeros(num_blocks, num_heads, head_size, block_size, dtype=dtype, device=device)
+        self.free_blocks = collections.deque(range(num_blocks))
+        # host mirrors (authoritative) and device copies read by the kernels
+        self.h_tables = np.full((num_layers, max_seqs, max_blocks_per_seq), -1, dtype=np.int32)
+        self.h_lens = np.zeros(max_seqs, dtype=np.int32)
+        self.active = np.zeros(max_seqs, dtype=bool)
+        self.d_tables = torch.full((num_layers, max_seqs, max_blocks_per_seq), -1, dtype=torch.int32, device=device)
+        self.d_lens = torch.zeros(max_seqs, dtype=torch.int32, device=device)       # seq_lens passed to attention
+        self.d_slots = torch.full((num_layers, max_seqs), -1, dtype=torch.int64, device=device)
+        self._pin_slots = torch.empty((num_layers, max_seqs), dtype=torch.int64).pin_memory() \
+            if device.type == "cuda" else torch.empty((num_layers, max_seqs), dtype=torch.int64)
+        self._pin_lens = torch.empty(max_seqs, dtype=torch.int32).pin_memory() \
+            if device.type == "cuda" else torch.empty(max_seqs, dtype=torch.int32)
+
+    # -- allocation ---------------------------------------------------------------------------
+    def _take(self, n: int) -> List[int]:
+        if len(self.free_blocks) < n:
+            raise RuntimeError("No free blocks available")            # kv_cache.py:22-23, 57-58
+        return [self.free_blocks.popleft() for _ in range(n)]
+
+    def add_sequence(self, seq: int, prompt_len: int) -> List[torch.Tensor]:
+        """Allocate blocks for a prompt; returns the per-layer int64 slot mappings [prompt_len]
+        (reference: kv_cache.py:21-37, slot = block * B + offset)."""
+        assert not self.active[seq] and 0 < prompt_len <= self.max_blocks_per_seq * self.block_size
+        B = self.block_size
+        nblk = (prompt_len + B - 1) // B
+        pos = np.arange(prompt_len)
+        mappings = []
+        for l in range(self.num_layers):
+            blocks = np.asarray(self._take(nblk), dtype=np.int32)
+            self.h_tables[l, seq, :nblk] = blocks
+            mappings.append(torch.from_numpy(blocks[pos // B].astype(np.int64) * B + pos % B).to(self.device))
+        self.h_lens[seq] = prompt_len
+        self.active[seq] = True
+        self.d_tables[:, seq].copy_(torch.from_numpy(self.h_tables[:, seq]), non_blocking=True)
+        return mappings
+
+    def free(self, seq: int) -> None:
+        """Return a sequence's blocks to the BACK of the free list (kv_cache.py:81-86)."""
+        if not self.active[seq]:
+            return
+        used = self.h_tables[:, seq][self.h_tables[:, seq] >= 0]
+        self.free_blocks.extend(int(b) for b in used)
+        self.h_tables[:, seq] = -1
+        self.h_lens[seq] = 0
+        self.active[seq] = False
+        self.d_tables[:, seq].fill_(-1)
+
+    # -- one decode step for every active sequence ----------------------------------------------
+    def begin_decode_step(self, attend_to_new_token: bool = True) -> None:
+        """Reserve the slot of the token being decoded for every active sequence and publish
+        `d_slots` [L, S], `d_tables`, `d_lens` for the kernels.  Batched counterpart of
+        BlockManager.decode_step (block_manager.py:28-63): when a sequence's last block is full a
+        new block is appended per layer (kv_cache.py:56-73).  Inactive rows get slot -1 (skipped by
+        reshape_and_cache, cache_kernels.cu:166-169) and seq_len 0 (zeros from attention).
+
+        attend_to_new_token=False reproduces the reference scheduler's off-by-one (it passes
+        seq_lens = L after writing slot L, scheduler.py:96-101, so the new token does not attend to
+        itself); True attends over L + 1 tokens like ordinary causal decoding."""
+        B = self.block_size
+        act = np.nonzero(self.active)[0]
+        pos = self.h_lens[act].astype(np.int64)                    # position of the new token
+        if (pos >= self.max_blocks_per_seq * B).any():
+            raise RuntimeError("sequence exceeds max_blocks_per_seq * block_size")
+        need = act[pos % B == 0]                                    # last block full (or empty): append one
+        if need.size:
+            idx = (self.h_lens[need] // B).astype(np.int64)
+            new_blocks = np.asarray(self._take(need.size * self.num_layers), dtype=np.int32)
+            new_blocks = new_blocks.reshape(self.num_layers, need.size)
+            self.h_tables[:, need, idx] = new_blocks
+            l_idx = torch.arange(self.num_layers, device=self.device)[:, None]
+            self.d_tables[l_idx, torch.from_numpy(need).to(self.device)[None, :],
+                          torch.from_numpy(idx).to(self.device)[None, :]] = torch.from_numpy(new_blocks).to(self.device)
+        slots = np.full((self.num_layers, self.max_seqs), -1, dtype=np.int64)
+        blk = self.h_tables[:, act, pos // B].astype(np.int64)      # [L, n_act]
+        slots[:, act] = blk * B + pos % B
+        lens = np.zeros(self.max_seqs, dtype=np.int32)
+        lens[act] = self.h_lens[act] + (1 if attend_to_new_token else 0)
+        self._pin_slots.copy_(torch.from_numpy(slots))
+        self._pin_lens.copy_(torch.from_numpy(lens))
+        self.d_slots.copy_(self._pin_slots, non_blocking=True)
+        self.d_lens.copy_(self._pin_lens, non_blocking=True)
+        self.h_lens[act] += 1
+
+    def positions(self) -> np.ndarray:
+        """Position id of the token being decoded in the step begun last (0 for inactive rows)."""
+        p = np.zeros(self.max_seqs, dtype=np.int64)
+        p[self.active] = self.h_lens[self.active] - 1
+        return p
+
+
+# ---------------------------------------------------------------------------------------------
+# model
+# ---------------------------------------------------------------------------------------------
+def synthetic_gpt2_state_dict(shape: GPT2Shape, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Seeded random-init weights under the reference model's parameter names (no network: the HF
+    checkpoint gpt2.py:276-331 loads cannot be downloaded).  CPU generator => identical on every box.
+    Scale 0.02 like GPT-2's initialiser, LayerNorm weight ~ 1."""
+    g = torch.Generator().manual_seed(seed)
+    E, V, P = shape.n_embd, shape.vocab_size, shape.n_positions
+
+    def rnd(*s, std=0.02):
+        return (torch.randn(*s, generator=g) * std).to(dtype)
+
+    sd = {"transformer.wte.weight": rnd(V, E), "transformer.wpe.weight": rnd(P, E, std=0.01),
+          "transformer.ln_f.weight": (1 + rnd(E)).to(dtype), "transformer.ln_f.bias": rnd(E)}
+    for i in range(shape.n_layer):
+        p = f"transformer.h.{i}."
+        sd.update({
+            p + "ln_1.weight": (1 + rnd(E)).to(dtype), p + "ln_1.bias": rnd(E),
+            p + "attn.c_attn.weight": rnd(3 * E, E), p + "attn.c_attn.bias": rnd(3 * E),
+            p + "attn.c_proj.weight": rnd(E, E, std=0.02 / math.sqrt(2 * shape.n_layer)), p + "attn.c_proj.bias": rnd(E),
+            p + "ln_2.weight": (1 + rnd(E)).to(dtype), p + "ln_2.bias": rnd(E),
+            p + "mlp.c_fc.weight": rnd(4 * E, E), p + "mlp.c_fc.bias": rnd(4 * E),
+            p + "mlp.c_proj.weight": rnd(E, 4 * E, std=0.02 / math.sqrt(2 * shape.n_layer)), p + "mlp.c_proj.bias": rnd(E),
+        })
+    sd["lm_head.weight"] = sd["transformer.wte.weight"]                 # tied (gpt2.py:247)
+    return sd
+
+
+class GPT2Decoder:
+    """GPT-2 forward for serving: prefill (eager causal attention, like gpt2.py:46-59, 71-78) and
+    batched single-token decode through the paged-attention hot path.
+
+    Parameter names and shapes are the reference GPT2LMHeadModel's (nn.Linear [out, in] weights,
+    exact-erf GELU as gpt2.py:123), so `load_state_dict` accepts a reference state_dict."""
+
+    def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16):
+        self.shape, self.device, self.dtype = shape, device, dtype
+        self.w: Dict[str, torch.Tensor] = {}
+        self.scale = shape.head_size ** -0.5
+        self._graph = None
+
+    # -- weights -----------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.w = {k: v.detach().to(device=self.device, dtype=self.dtype).contiguous() for k, v in sd.items()
+                  if k != "lm_head.weight"}
+        self.w["lm_head.weight"] = self.w["transformer.wte.weight"]
+        self._graph = None
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return self.w
+
+    def broadcast_weights(self, src: int = 0) -> None:
+        """The path's only collective: replicate the weights from rank `src` (NCCL over NVLink)."""
+        from . import sharding
+        sharding.broadcast_state_dict(self.w, src=src)
+
+    # -- building blocks -----------------------------------------------------------------------
+    def _ln(self, x, prefix):
+        return F.layer_norm(x, (self.shape.n_embd,), self.w[prefix + ".weight"], self.w[prefix + ".bias"],
+                            self.shape.layer_norm_epsilon)
+
+    def _mlp(self, x, p):
+        h = F.linear(x, self.w[p + "mlp.c_fc.weight"], self.w[p + "mlp.c_fc.bias"])
+        return F.linear(F.gelu(h), self.w[p + "mlp.c_proj.weight"], self.w[p + "mlp.c_proj.bias"])
+
+    # -- prefill: one sequence, eager causal attention + reshape_and_cache -----------------------
+    @torch.no_grad()
+    def prefill(self, input_ids: torch.Tensor, kv: BatchedKVState, seq: int) -> torch.Tensor:
+        """input_ids [T] -> logits of the last position [vocab].  K/V of all T tokens are scattered
+        into the pool through the hot path's reshape_and_cache (gpt2.py:44)."""
+        s = self.shape
+        T = input_ids.numel()
+        H, D = s.n_head, s.head_size
+        slot_maps = kv.add_sequence(seq, T)
+        x = self.w["transformer.wte.weight"][input_ids] + self.w["transformer.wpe.weight"][:T]
+        mask = torch.full((T, T), float("-inf"), device=self.device, dtype=torch.float32).triu(1)
+        for i in range(s.n_layer):
+            p = f"transformer.h.{i}."
+            qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
+            q, k, v = (t.view(T, H, D) for t in qkv.split(s.n_embd, dim=-1))      # strided views, stride 3*E
+            ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, slot_maps[i], "auto", 1.0)
+            att = torch.matmul(q.transpose(0, 1).float(), k.transpose(0, 1).float().transpose(-1, -2)) * self.scale
+            att = torch.softmax(att + mask, dim=-1)
+            o = torch.matmul(att, v.transpose(0, 1).float()).transpose(0, 1).reshape(T, s.n_embd).to(self.dtype)
+            x = x + F.linear(o, self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
+            x = x + self._mlp(self._ln(x, p + "ln_2"), p)
+        x = self._ln(x[-1:], "transformer.ln_f")
+        return F.linear(x, self.w["lm_head.weight"])[0]
+
+    # -- decode: all sequences, one token each ----------------------------------------------------
+    @torch.no_grad()
+    def decode_forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, kv: BatchedKVState) -> torch.Tensor:
+        """input_ids, position_ids [S] (device) -> logits [S, vocab].  Uses kv.d_slots / d_tables /
+        d_lens as published by kv.begin_decode_step().  Per layer: reshape_and_cache then
+        paged_attention_v1 (gpt2.py:44, 62)."""
+        s = self.shape
+        S = input_ids.numel()
+        H, D, B = s.n_head, s.head_size, kv.block_size
+        max_seq_len = kv.max_blocks_per_seq * B                       # capacity, as scheduler.py:97
+        x = self.w["transformer.wte.weight"][input_ids] + self.w["transformer.wpe.weight"][position_ids]
+        for i in range(s.n_layer):
+            p = f"transformer.h.{i}."
+            qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
+            q, k, v = (t.view(S, H, D) for t in qkv.split(s.n_embd, dim=-1))
+            ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], "auto", 1.0)
+            o = torch.empty((S, H, D), dtype=self.dtype, device=self.device)
+            ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[i], kv.d_lens,
+                                   B, max_seq_len, None, "auto", 1.0, 0, 0, 1, 1, 0)
+            x = x + F.linear(o.view(S, s.n_embd), self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
+            x = x + self._mlp(self._ln(x, p + "ln_2"), p)
+        return F.linear(self._ln(x, "transformer.ln_f"), self.w["lm_head.weight"])
+
+    # -- CUDA-graph capture of the decode step -----------------------------------------------------
+    def capture_decode_graph(self, kv: BatchedKVState) -> None:
+        """Capture decode_forward + greedy argmax for kv.max_seqs rows into one CUDA graph.  Inputs
+        live in static buffers (`g_ids`, `g_pos`, and kv.d_slots / d_tables / d_lens, which
+        begin_decode_step updates in place); outputs in `g_logits`, `g_next`."""
+        S = kv.max_seqs
+        self.g_ids = torch.zeros(S, dtype=torch.int64, device=self.device)
+        self.g_pos = torch.zeros(S, dtype=torch.int64, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                                   # warm-up outside capture
+            for _ in range(2):
+                self.g_logits = self.decode_forward(self.g_ids, self.g_pos, kv)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.g_logits = self.decode_forward(self.g_ids, self.g_pos, kv)
+            self.g_next = torch.argmax(self.g_logits, dim=-1)
+
+    def replay_decode_graph(self) -> torch.Tensor:
+        self._graph.replay()
+        return self.g_next
+
+
+# ---------------------------------------------------------------------------------------------
+# greedy generation loop (harness)
+# ---------------------------------------------------------------------------------------------
+@torch.no_grad()
+def greedy_generate(model: GPT2Decoder, kv: BatchedKVState, prompts: Sequence[Sequence[int]], max_new_tokens: int,
+                    use_graph: bool = False) -> List[List[int]]:
+    """Prefill every prompt, then decode all sequences together, greedy argmax.  Returns the new
+    token ids per prompt.  The only device->host transfer is the final read of the ids."""
+    dev = model.device
+    n = len(prompts)
+    assert n <= kv.max_seqs
+    first = torch.zeros(kv.max_seqs, dtype=torch.int64, device=dev)
+    for i, pr in enumerate(prompts):
+        logits = model.prefill(torch.tensor(list(pr), dtype=torch.int64, device=dev), kv, i)
+        first[i] = torch.argmax(logits)
+    out = [first.clone()]
+    cur = first
+    if use_graph and max_new_tokens > 1:
+        model.capture_decode_graph(kv)
+    for _ in range(max_new_tokens - 1):
+        kv.begin_decode_step(attend_to_new_token=True)
+        pos = torch.from_numpy(kv.positions()).to(dev, non_blocking=True)
+        if use_graph:
+            model.g_ids.copy_(cur)
+            model.g_pos.copy_(pos)
+            cur = model.replay_decode_graph().clone()
+        else:
+            cur = torch.argmax(model.decode_forward(cur, pos, kv), dim=-1)
+        out.append(cur)
+    ids = torch.stack(out, dim=1)[:n].cpu().tolist()
+    return ids
