@@ -60,9 +60,11 @@ enum {
  *   scale      softmax scale (head_size ** -0.5 in vllmini, gpt2.py:13)
  *   max_seq_len upper bound on seq_lens[] (vllmini passes capacity, scheduler.py:97); used only
  *                to pick the split-KV factor
- *   workspace  optional device scratch for split-KV partials; may be NULL (=> no split).
- *                Must be zero-filled once before its first use; the kernel leaves it reusable.
- *                Size from vb200_paged_attention_v1_workspace_bytes().
+ *   workspace  optional device scratch: ticket words of the persistent kernel's dynamic unit
+ *                scheduler and split-KV counters/partials; may be NULL (=> static unit assignment,
+ *                no split).  16-byte aligned; must be zero-filled once before its first use; the
+ *                kernel leaves it reusable; one workspace must not be shared by launches that can
+ *                run concurrently.  Size from vb200_paged_attention_v1_workspace_bytes().
  *   device     CUDA device ordinal the pointers live on (reference: OptionalCUDAGuard, :736)
  *   stream     cudaStream_t (reference: at::cuda::getCurrentCUDAStream(), :737)
  *
@@ -76,8 +78,8 @@ int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_c
                                  int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
                                  size_t workspace_bytes, int32_t device, void* stream);
 
-/* Bytes of split-KV workspace that lets the launcher use its preferred split factor for this
- * problem shape (0 when it would not split). */
+/* Bytes of workspace that lets the launcher use dynamic unit scheduling (64 KiB of ticket / counter
+ * words, always) and its preferred split-KV factor for this problem shape (partials, when it splits). */
 size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
                                                 int32_t block_size, int32_t max_seq_len);
 

@@ -77,8 +77,9 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.vb200_reshape_and_cache_f16(one, one, one, one, one, 0, 12, 64, 16, 8, 768, 768, 0, None) == 0
     assert lib.vb200_reshape_and_cache_f16(one, one, one, one, one, 1, 12, 64, 16, 7, 768, 768, 0, None) == -4
     assert lib.vb200_reshape_and_cache_f16(None, one, one, one, one, 1, 12, 64, 16, 8, 768, 768, 0, None) == -4
-    assert lib.vb200_paged_attention_v1_workspace_bytes(256, 12, 64, 16, 1024) == 0      # big batch: no split
-    assert lib.vb200_paged_attention_v1_workspace_bytes(1, 12, 64, 16, 8192) > 0         # tiny batch: split-KV
+    base = lib.vb200_paged_attention_v1_workspace_bytes(256, 12, 64, 16, 1024)           # big batch: no split,
+    assert base == 16384 * 4                                                              # only the ticket/counter words
+    assert lib.vb200_paged_attention_v1_workspace_bytes(1, 12, 64, 16, 8192) > base      # tiny batch: split-KV partials
 
 
 def test_dropin_surface_matches_reference_package():

@@ -116,7 +116,7 @@ def test_paged_attention_vs_oracle_and_reference_kernel(name, ref_ext):
             f"{name}: new kernel further from truth ({err_new:.3e}) than the reference kernel ({err_ref:.3e})"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("force_splits", [0, 2, 5])
 def test_pipeline_variants_and_split_kv_agree(variant, force_splits):
     from vllmini_b200 import _native
@@ -142,7 +142,7 @@ def test_small_batch_long_context_uses_split_kv():
     q, kc, vc, bt, sl = po.make_case(2, 12, 64, 16, lens, seed=21)
     c = dict(S=2, H=12, D=64, B=16, q=q, kc=kc, vc=vc, bt=bt, sl=sl, scale=0.125)
     from vllmini_b200 import _native
-    assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) > 0
+    assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) > 16384 * 4
     got = run_cuda_attention(c)
     truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, mode="exact").astype(np.float64)
     assert_close_to_truth(got, truth, what="split-KV")

@@ -65,6 +65,7 @@ struct PaCfg {
   static constexpr int BAR_OFF = PBUF_OFF + W * 64;         // W * NST mbarriers
   static constexpr int RED_OFF = BAR_OFF + W * NST * 8;     // W * (D + 2) floats
   static constexpr int SMEM = RED_OFF + W * (D + 2) * 4;
+  static constexpr int kD = D, kB = B;
   static_assert(B == 8 || B == 16 || B == 32, "block size");
   static_assert(D % 8 == 0 && NJ >= 1 && (D * B) % 256 == 0, "head size");
 };
@@ -92,10 +93,242 @@ __device__ __forceinline__ uint4 keep_first(uint4 v, int nv) {
   return make_uint4(word(v.x, 0), word(v.y, 1), word(v.z, 2), word(v.w, 3));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared device pieces
+// ---------------------------------------------------------------------------------------------
+
+// One 32-token stage resident in shared memory at `sbase` (K tiles then V tiles): QK^T, online
+// softmax update of (m, lsum), PV accumulation into acc[].  Warp-synchronous; `pbuf` is the warp's
+// 64-byte fp16 probability buffer.  Ends with a __syncwarp(): afterwards every lane is done with the
+// stage's shared memory and with pbuf.
+template <class C>
+__device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int lane, const uint4 (&qv)[C::NJ],
+                                              float& m, float& lsum, float (&acc)[C::NJ], int stage_tok0, int tok_end,
+                                              float scale_log2e) {
+  constexpr int B = C::kB;
+  // ---- QK^T: lane owns token lane % B of every block of the stage ----
+  float part[C::BPS];
+#pragma unroll
+  for (int b = 0; b < C::BPS; ++b) {
+    float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) {
+      const uint4 kv = lds128(sbase + b * C::TILE + (lane + 32 * j) * 16);
+      dot8(qv[j], kv, c0, c1);
+    }
+    part[b] = c0 + c1;
+  }
+  // transpose-reduce: sum over the BPS lanes sharing lane % B; lane keeps block lane / B
+  float s;
+  if constexpr (C::BPS == 1) {
+    s = part[0];
+  } else if constexpr (C::BPS == 2) {
+    const bool up = lane & 16;
+    const float give = up ? part[0] : part[1];
+    s = (up ? part[1] : part[0]) + __shfl_xor_sync(0xffffffffu, give, 16);
+  } else {  // BPS == 4
+    const bool up = lane & 16;
+    const float g0 = up ? part[0] : part[2];
+    const float g1 = up ? part[1] : part[3];
+    const float k0 = (up ? part[2] : part[0]) + __shfl_xor_sync(0xffffffffu, g0, 16);
+    const float k1 = (up ? part[3] : part[1]) + __shfl_xor_sync(0xffffffffu, g1, 16);
+    const bool up2 = lane & 8;
+    const float give = up2 ? k0 : k1;
+    s = (up2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+  // lane now holds the logit of stage token `lane`
+  const bool tail = stage_tok0 + 32 > tok_end;  // warp-uniform
+  s *= scale_log2e;
+  if (stage_tok0 + lane >= tok_end) s = -INFINITY;  // select, so NaN garbage cannot leak
+
+  // ---- online softmax (warp-uniform running max) ----
+  const float smax = warp_max_f32(s);
+  if (smax > m) {
+    const float alpha = ex2(m - smax);  // m = -inf on first use -> 0
+    m = smax;
+    lsum *= alpha;
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) acc[j] *= alpha;
+  }
+  const __half p16 = __float2half_rn(ex2(s - m));
+  lsum += __half2float(p16);  // normalise by the weights actually applied
+  sts16(pbuf + lane * 2, __half_as_ushort(p16));
+  __syncwarp();
+
+  // ---- PV: lane owns rows lane/TPR + j*(32/TPR), tokens 8*(lane%TPR)..+7 of each block ----
+#pragma unroll
+  for (int b = 0; b < C::BPS; ++b) {
+    const uint4 pv = lds128(pbuf + (b * B + (lane % C::TPR) * 8) * 2);
+    float c1[C::NJ];
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) c1[j] = 0.f;
+    if (!tail) {
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) {
+        const uint4 vv = lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16);
+        dot8(pv, vv, acc[j], c1[j]);
+      }
+    } else {
+      const int nv = tok_end - (stage_tok0 + b * B + (lane % C::TPR) * 8);
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) {
+        const uint4 vv = keep_first(lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16), nv);
+        dot8(pv, vv, acc[j], c1[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) acc[j] += c1[j];
+  }
+  __syncwarp();
+}
+
+// Issue the bulk copies of one stage: lane i < 2*BPS issues copy i (K tiles 0..BPS-1, then V tiles).
+// `phys`: lane b < BPS holds the physical block id of block b of the stage; nb = blocks that exist.
+template <class C>
+__device__ __forceinline__ void issue_stage_copies(uint32_t dst_stage, uint32_t bar, int lane, int phys, int nb,
+                                                   const __half* kbase, const __half* vbase,
+                                                   int64_t kv_block_stride) {
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * nb * C::TILE));
+  __syncwarp();
+  const int b = lane % C::BPS;
+  const int is_v = lane / C::BPS;
+  const int phys_b = __shfl_sync(0xffffffffu, phys, b);
+  if (lane < 2 * C::BPS && b < nb) {
+    const __half* src = (is_v ? vbase : kbase) + (int64_t)phys_b * kv_block_stride;
+    bulk_g2s(dst_stage + (is_v * C::BPS + b) * C::TILE, src, C::TILE, bar);
+  }
+}
+
+// Warp totals -> red[warp][D + 2] = {acc rows..., m, lsum}
+template <class C>
+__device__ __forceinline__ void warp_publish(float* red, int warp, int lane, float m, float lsum,
+                                             float (&acc)[C::NJ]) {
+  constexpr int D = C::kD;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+#pragma unroll
+  for (int j = 0; j < C::NJ; ++j) {
+#pragma unroll
+    for (int o = C::TPR / 2; o >= 1; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane % C::TPR == 0) {
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) red[warp * (D + 2) + lane / C::TPR + j * (32 / C::TPR)] = acc[j];
+  }
+  if (lane == 0) {
+    red[warp * (D + 2) + D] = m;
+    red[warp * (D + 2) + D + 1] = lsum;
+  }
+}
+
+// CTA-level log-sum-exp merge of the W warps' partials (after a barrier), then either the final
+// normalised fp16 row (nsplit_seq == 1) or a split-KV partial + last-arriver merge.
+// `tid` in [0, W*32); BAR = named barrier id used by the W*32 compute threads.
+template <class C, int W, int BAR>
+__device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const float* red, int tid, int seq, int head,
+                                                    int split, int nsplit_seq, int* s_last) {
+  constexpr int D = C::kD;
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < W; ++w) M = fmaxf(M, red[w * (D + 2) + D]);
+  float L = 0.f;
+  float wgt[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const float mw = red[w * (D + 2) + D];
+    wgt[w] = (mw == -INFINITY) ? 0.f : ex2(mw - M);
+    L += red[w * (D + 2) + D + 1] * wgt[w];
+  }
+  const int64_t row = (int64_t)seq * p.num_heads + head;
+
+  if (nsplit_seq == 1) {
+    // reference normaliser: 1 / (sum + 1e-6)  (attention_kernels.cu:342)
+    const float inv = __fdividef(1.f, L + 1e-6f);
+    for (int d = tid; d < D; d += W * 32) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
+      p.out[row * D + d] = __float2half_rn(o * inv);
+    }
+    return;
+  }
+
+  // ---- split-KV: publish the partial, last arriver of this (seq, head) merges ----
+  {
+    const int64_t part_idx = row * p.num_splits + split;
+    for (int d = tid; d < D; d += W * 32) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
+      p.ws_o[part_idx * D + d] = o;
+    }
+    if (tid == 0) {
+      p.ws_ml[part_idx * 2] = M;
+      p.ws_ml[part_idx * 2 + 1] = L;
+    }
+  }
+  __threadfence();
+  named_bar_sync<BAR, W * 32>();
+  if (tid == 0) {
+    const int prev = atomicAdd(p.ws_cnt + row, 1);
+    *s_last = (prev == nsplit_seq - 1);
+    if (prev == nsplit_seq - 1) p.ws_cnt[row] = 0;  // leave the workspace reusable
+  }
+  named_bar_sync<BAR, W * 32>();
+  if (!*s_last) return;
+  __threadfence();
+  {
+    const float* ml = p.ws_ml + row * p.num_splits * 2;
+    float Mg = -INFINITY;
+    for (int i = 0; i < nsplit_seq; ++i) Mg = fmaxf(Mg, ld_cg_f32(ml + 2 * i));
+    float Lg = 0.f;
+    for (int i = 0; i < nsplit_seq; ++i) {
+      const float mi = ld_cg_f32(ml + 2 * i);
+      Lg += ld_cg_f32(ml + 2 * i + 1) * ((mi == -INFINITY) ? 0.f : ex2(mi - Mg));
+    }
+    const float inv = __fdividef(1.f, Lg + 1e-6f);
+    for (int d = tid; d < D; d += W * 32) {
+      float o = 0.f;
+      for (int i = 0; i < nsplit_seq; ++i) {
+        const float mi = ld_cg_f32(ml + 2 * i);
+        const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
+        o += ld_cg_f32(p.ws_o + (row * p.num_splits + i) * D + d) * wi;
+      }
+      p.out[row * D + d] = __float2half_rn(o * inv);
+    }
+  }
+}
+
+// Token range of (seq, split) and derived counts.
+struct UnitRange {
+  int tok_begin, tok_end, nstages, nblk, nsplit_seq;
+  bool empty_split;  // split > 0 and no token in it: nothing to do, nobody waits for it
+};
+template <int B>
+__device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int split) {
+  int len = p.seq_lens[seq];
+  len = len < p.max_blocks_per_seq * B ? len : p.max_blocks_per_seq * B;  // never read past the table row
+  if (p.num_splits > 1 && len > p.num_splits * p.split_tokens) len = p.num_splits * p.split_tokens;
+  UnitRange r;
+  r.tok_begin = p.num_splits > 1 ? split * p.split_tokens : 0;
+  r.empty_split = split > 0 && r.tok_begin >= len;
+  r.tok_end = len;
+  if (p.num_splits > 1 && r.tok_begin + p.split_tokens < len) r.tok_end = r.tok_begin + p.split_tokens;
+  const int ntok = r.tok_end > r.tok_begin ? r.tok_end - r.tok_begin : 0;
+  r.nstages = (ntok + 31) >> 5;
+  r.nblk = (ntok + B - 1) / B;
+  r.nsplit_seq = p.num_splits > 1 && len > 0 ? (len + p.split_tokens - 1) / p.split_tokens : 1;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classic kernel: one CTA per (head, seq, split)
+// ---------------------------------------------------------------------------------------------
 template <int D, int B, int W, int NST>
 __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   using C = PaCfg<D, B, W, NST>;
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_last;
 
   const int head = blockIdx.x;
   const int seq = blockIdx.y;
@@ -103,20 +336,12 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
-  int len = p.seq_lens[seq];
-  len = len < p.max_blocks_per_seq * B ? len : p.max_blocks_per_seq * B;  // never read past the table row
-  if (p.num_splits > 1 && len > p.num_splits * p.split_tokens) len = p.num_splits * p.split_tokens;
-  const int tok_begin = p.num_splits > 1 ? split * p.split_tokens : 0;
-  if (split > 0 && tok_begin >= len) return;  // this split holds no token (split 0 always runs)
-  int tok_end = len;
-  if (p.num_splits > 1 && tok_begin + p.split_tokens < len) tok_end = tok_begin + p.split_tokens;
-  const int ntok = tok_end > tok_begin ? tok_end - tok_begin : 0;
-  const int nstages = (ntok + 31) >> 5;
-  const int nblk = (ntok + B - 1) / B;
-  const int nsplit_seq = p.num_splits > 1 && len > 0 ? (len + p.split_tokens - 1) / p.split_tokens : 1;
+  const UnitRange r = unit_range<B>(p, seq, split);
+  if (r.empty_split) return;
+  const int nstages = r.nstages, nblk = r.nblk;
 
   const int kv_head = head / (p.num_heads / p.num_kv_heads);
-  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + tok_begin / B;
+  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + r.tok_begin / B;
   const __half* kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
   const __half* vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
 
@@ -131,22 +356,10 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   }
   __syncthreads();
 
-  // ---- producer side: lane i < 2*BPS issues copy i of a stage (K tiles 0..BPS-1, then V tiles) ----
-  // phys: lane b < BPS holds the physical block id of block b of the stage being issued.
   auto issue_stage = [&](int st, int slot, int phys) {
     const int blk0 = st * C::BPS;
-    const int nb = nblk - blk0 < C::BPS ? nblk - blk0 : C::BPS;  // blocks that exist in this stage
-    const uint32_t bar = bars + slot * 8;
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * nb * C::TILE));
-    __syncwarp();
-    const int b = lane % C::BPS;
-    const int is_v = lane / C::BPS;
-    const int phys_b = __shfl_sync(0xffffffffu, phys, b);
-    if (lane < 2 * C::BPS && b < nb) {
-      const __half* src = (is_v ? vbase : kbase) + (int64_t)phys_b * p.kv_block_stride;
-      const uint32_t dst = ring + slot * C::STAGE + (is_v * C::BPS + b) * C::TILE;
-      bulk_g2s(dst, src, C::TILE, bar);
-    }
+    const int nb = nblk - blk0 < C::BPS ? nblk - blk0 : C::BPS;
+    issue_stage_copies<C>(ring + slot * C::STAGE, bars + slot * 8, lane, phys, nb, kbase, vbase, p.kv_block_stride);
   };
   auto load_phys = [&](int st) -> int {  // table entries of stage st, one per lane < BPS
     const int blk = st * C::BPS + lane;
@@ -181,85 +394,9 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   int k = 0;
   for (int st = warp; st < nstages; st += W, ++k) {
     const int slot = k % NST;
-    const uint32_t sbase = ring + slot * C::STAGE;
     mbar_wait(bars + slot * 8, (k / NST) & 1);
-
-    // ---- QK^T: lane owns token lane % B of every block of the stage ----
-    float part[C::BPS];
-#pragma unroll
-    for (int b = 0; b < C::BPS; ++b) {
-      float c0 = 0.f, c1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) {
-        const uint4 kv = lds128(sbase + b * C::TILE + (lane + 32 * j) * 16);
-        dot8(qv[j], kv, c0, c1);
-      }
-      part[b] = c0 + c1;
-    }
-    // transpose-reduce: sum over the BPS lanes sharing lane % B; lane keeps block lane / B
-    float s;
-    if constexpr (C::BPS == 1) {
-      s = part[0];
-    } else if constexpr (C::BPS == 2) {
-      const bool up = lane & 16;
-      const float give = up ? part[0] : part[1];
-      s = (up ? part[1] : part[0]) + __shfl_xor_sync(0xffffffffu, give, 16);
-    } else {  // BPS == 4
-      const bool up = lane & 16;
-      const float g0 = up ? part[0] : part[2];
-      const float g1 = up ? part[1] : part[3];
-      const float k0 = (up ? part[2] : part[0]) + __shfl_xor_sync(0xffffffffu, g0, 16);
-      const float k1 = (up ? part[3] : part[1]) + __shfl_xor_sync(0xffffffffu, g1, 16);
-      const bool up2 = lane & 8;
-      const float give = up2 ? k0 : k1;
-      s = (up2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, give, 8);
-    }
-    // lane now holds the logit of stage token `lane`
-    const int stage_tok0 = tok_begin + st * 32;
-    const bool tail = stage_tok0 + 32 > tok_end;  // warp-uniform
-    s *= p.scale_log2e;
-    if (stage_tok0 + lane >= tok_end) s = -INFINITY;  // select, so NaN garbage cannot leak
-
-    // ---- online softmax (warp-uniform running max) ----
-    const float smax = warp_max_f32(s);
-    if (smax > m) {
-      const float alpha = ex2(m - smax);  // m = -inf on first use -> 0
-      m = smax;
-      lsum *= alpha;
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) acc[j] *= alpha;
-    }
-    const __half p16 = __float2half_rn(ex2(s - m));
-    lsum += __half2float(p16);  // normalise by the weights actually applied
-    sts16(pbuf + lane * 2, __half_as_ushort(p16));
-    __syncwarp();
-
-    // ---- PV: lane owns rows lane/TPR + j*(32/TPR), tokens 8*(lane%TPR)..+7 of each block ----
-#pragma unroll
-    for (int b = 0; b < C::BPS; ++b) {
-      const uint4 pv = lds128(pbuf + (b * B + (lane % C::TPR) * 8) * 2);
-      float c1[C::NJ];
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) c1[j] = 0.f;
-      if (!tail) {
-#pragma unroll
-        for (int j = 0; j < C::NJ; ++j) {
-          const uint4 vv = lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16);
-          dot8(pv, vv, acc[j], c1[j]);
-        }
-      } else {
-        const int nv = tok_end - (stage_tok0 + b * B + (lane % C::TPR) * 8);
-#pragma unroll
-        for (int j = 0; j < C::NJ; ++j) {
-          const uint4 vv = keep_first(lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16), nv);
-          dot8(pv, vv, acc[j], c1[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) acc[j] += c1[j];
-    }
-    __syncwarp();  // every lane is done with this slot and with pbuf
-
+    process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, m, lsum, acc, r.tok_begin + st * 32, r.tok_end,
+                     p.scale_log2e);
     // ---- refill this slot with the stage NST rounds ahead ----
     const int st_next = st + NST * W;
     if (st_next < nstages) {
@@ -268,102 +405,214 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
     }
   }
 
-  // ---- per-warp totals -> smem ----
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-#pragma unroll
-  for (int j = 0; j < C::NJ; ++j) {
-#pragma unroll
-    for (int o = C::TPR / 2; o >= 1; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-  }
   float* red = reinterpret_cast<float*>(smem + C::RED_OFF);  // [W][D + 2]
-  if (lane % C::TPR == 0) {
+  warp_publish<C>(red, warp, lane, m, lsum, acc);
+  __syncthreads();
+  cta_merge_and_store<C, W, 1>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent kernel: grid = resident CTAs; each CTA pulls (seq, head, split) units from a global
+// ticket counter and its warps keep their bulk-copy rings full ACROSS unit boundaries, so the
+// per-unit prologue (metadata, table, first-copy latency) and epilogue (merge, store) overlap the
+// streaming of the next unit.  Warps 0..W-1 compute; warp W is the scheduler: lane 0 fetches
+// tickets, resolves unit metadata (seq_len load, split range) and publishes it through a ring of NU
+// shared-memory descriptors guarded by full/empty mbarriers, running up to NU units ahead.
+// ---------------------------------------------------------------------------------------------
+struct UnitDesc {  // 32 bytes
+  int seq, head, split, tok_begin, tok_end, nstages, nsplit_seq, valid;
+};
+constexpr int kNU = 4;
+
+template <int D, int B, int W, int NST>
+struct PaPersistCfg : PaCfg<D, B, W, NST> {
+  using Base = PaCfg<D, B, W, NST>;
+  static constexpr int RED2_OFF = Base::RED_OFF;                           // 2 x W x (D + 2) floats
+  static constexpr int UNIT_OFF = RED2_OFF + 2 * W * (D + 2) * 4;          // kNU descriptors
+  static constexpr int UBAR_OFF = UNIT_OFF + kNU * (int)sizeof(UnitDesc);  // full[kNU], empty[kNU]
+  static constexpr int SMEM = UBAR_OFF + 2 * kNU * 8 + 16;
+};
+
+template <int D, int B, int W, int NST>
+__global__ void __launch_bounds__((W + 1) * 32) pa_v1_persistent_kernel(const PaParams p, const int num_units,
+                                                                       int* __restrict__ sched) {
+  using C = PaPersistCfg<D, B, W, NST>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  UnitDesc* units = reinterpret_cast<UnitDesc*>(smem + C::UNIT_OFF);
+  const uint32_t ufull = smem_u32(smem + C::UBAR_OFF);
+  const uint32_t uempty = ufull + kNU * 8;
+  int* s_last = reinterpret_cast<int*>(smem + C::UBAR_OFF + 2 * kNU * 8);
+
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int j = 0; j < C::NJ; ++j) red[warp * (D + 2) + lane / C::TPR + j * (32 / C::TPR)] = acc[j];
-  }
-  if (lane == 0) {
-    red[warp * (D + 2) + D] = m;
-    red[warp * (D + 2) + D + 1] = lsum;
+    for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + C::BAR_OFF) + i * 8, 1);
+#pragma unroll
+    for (int i = 0; i < kNU; ++i) {
+      mbar_init(ufull + i * 8, 1);
+      mbar_init(uempty + i * 8, W);
+    }
+    fence_mbar_init();
   }
   __syncthreads();
 
-  // ---- merge the W warps (log-sum-exp) ----
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < W; ++w) M = fmaxf(M, red[w * (D + 2) + D]);
-  float L = 0.f;
-  float wgt[W];
-#pragma unroll
-  for (int w = 0; w < W; ++w) {
-    const float mw = red[w * (D + 2) + D];
-    wgt[w] = (mw == -INFINITY) ? 0.f : ex2(mw - M);
-    L += red[w * (D + 2) + D + 1] * wgt[w];
-  }
-  const int64_t row = (int64_t)seq * p.num_heads + head;
-
-  if (nsplit_seq == 1) {
-    // reference normaliser: 1 / (sum + 1e-6)  (attention_kernels.cu:342)
-    const float inv = __fdividef(1.f, L + 1e-6f);
-    for (int d = threadIdx.x; d < D; d += W * 32) {
-      float o = 0.f;
-#pragma unroll
-      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
-      p.out[row * D + d] = __float2half_rn(o * inv);
+  // =================================== scheduler warp ===================================
+  if (warp == W) {
+    if (lane != 0) return;
+    const int H = p.num_heads, ns = p.num_splits;
+    int i = 0;  // descriptors published so far
+    for (int n = 0;; ++n) {
+      const int u = sched ? atomicAdd(sched, 1) : (int)blockIdx.x + n * (int)gridDim.x;
+      UnitDesc d;
+      d.valid = u < num_units;
+      d.seq = d.head = d.split = d.tok_begin = d.tok_end = d.nstages = 0;
+      d.nsplit_seq = 1;
+      if (d.valid) {
+        d.head = u % H;
+        const int rest = u / H;
+        d.split = rest % ns;
+        d.seq = rest / ns;
+        const UnitRange r = unit_range<B>(p, d.seq, d.split);
+        if (r.empty_split) continue;  // no token in this split: skip the ticket
+        d.tok_begin = r.tok_begin;
+        d.tok_end = r.tok_end;
+        d.nstages = r.nstages;
+        d.nsplit_seq = r.nsplit_seq;
+      }
+      const int e = i % kNU;
+      if (i >= kNU) mbar_wait(uempty + e * 8, ((i / kNU) - 1) & 1);
+      units[e] = d;
+      mbar_arrive(ufull + e * 8);  // release: descriptor visible to waiters
+      ++i;
+      if (!d.valid) break;
+    }
+    if (sched) {  // last CTA to run dry re-arms the ticket counter for the next launch
+      const int done = atomicAdd(sched + 1, 1);
+      if (done == (int)gridDim.x - 1) {
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+      }
     }
     return;
   }
 
-  // ---- split-KV: publish the partial, last arriver of this (seq, head) merges ----
-  {
-    const int64_t part_idx = row * p.num_splits + split;
-    for (int d = threadIdx.x; d < D; d += W * 32) {
-      float o = 0.f;
+  // =================================== compute warps ===================================
+  const uint32_t ring = smem_u32(smem) + warp * (NST * C::STAGE);
+  const uint32_t pbuf = smem_u32(smem + C::PBUF_OFF) + warp * 64;
+  const uint32_t bars = smem_u32(smem + C::BAR_OFF) + warp * (NST * 8);
+  float* red2 = reinterpret_cast<float*>(smem + C::RED2_OFF);
+  const int qpk = p.num_heads / p.num_kv_heads;
+
+  // producer state: unit pi (descriptor P), next stage pk of this warp's share, copies issued so far
+  int pi = -1, pk = 0, n_issued = 0, n_consumed = 0;
+  UnitDesc P;
+  P.valid = 1;
+  P.nstages = 0;
+  P.seq = P.head = P.split = P.tok_begin = P.tok_end = 0;
+  P.nsplit_seq = 1;
+  const int32_t* p_table = nullptr;
+  const __half* p_kbase = nullptr;
+  const __half* p_vbase = nullptr;
+  int p_nblk = 0;
+  int phys_pref = 0;  // table entries of P's stage pk (lane b < BPS), prefetched
+  uint4 q_next[C::NJ];
 #pragma unroll
-      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
-      p.ws_o[part_idx * D + d] = o;
+  for (int j = 0; j < C::NJ; ++j) q_next[j] = make_uint4(0, 0, 0, 0);
+  int ci = 0;  // consumer unit index
+
+  auto load_phys = [&](int st) -> int {
+    const int blk = st * C::BPS + lane;
+    return (lane < C::BPS && blk < p_nblk) ? __ldg(p_table + blk) : 0;
+  };
+  // move the producer to the next published unit; prefetch its q and first table entries
+  auto advance = [&]() {
+    ++pi;
+    pk = 0;
+    const int e = pi % kNU;
+    mbar_wait(ufull + e * 8, (pi / kNU) & 1);
+    P = units[e];
+    if (P.valid) {
+      const int kv_head = P.head / qpk;
+      p_table = p.block_tables + (int64_t)P.seq * p.max_blocks_per_seq + P.tok_begin / B;
+      p_kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
+      p_vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
+      const int ntok = P.tok_end - P.tok_begin;
+      p_nblk = ntok > 0 ? (ntok + B - 1) / B : 0;
+      const __half* qrow = p.q + (int64_t)P.seq * p.q_stride + (int64_t)P.head * D;
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) q_next[j] = ldg128(qrow + 8 * (lane / B + j * C::BPS));
+      phys_pref = (warp < P.nstages) ? load_phys(warp) : 0;
     }
-    if (threadIdx.x == 0) {
-      p.ws_ml[part_idx * 2] = M;
-      p.ws_ml[part_idx * 2 + 1] = L;
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  __shared__ int s_last;
-  if (threadIdx.x == 0) {
-    const int prev = atomicAdd(p.ws_cnt + row, 1);
-    s_last = (prev == nsplit_seq - 1);
-    if (s_last) p.ws_cnt[row] = 0;  // leave the workspace reusable
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    const float* ml = p.ws_ml + row * p.num_splits * 2;
-    float Mg = -INFINITY;
-    for (int i = 0; i < nsplit_seq; ++i) Mg = fmaxf(Mg, ld_cg_f32(ml + 2 * i));
-    float Lg = 0.f;
-    for (int i = 0; i < nsplit_seq; ++i) {
-      const float mi = ld_cg_f32(ml + 2 * i);
-      Lg += ld_cg_f32(ml + 2 * i + 1) * ((mi == -INFINITY) ? 0.f : ex2(mi - Mg));
-    }
-    const float inv = __fdividef(1.f, Lg + 1e-6f);
-    for (int d = threadIdx.x; d < D; d += W * 32) {
-      float o = 0.f;
-      for (int i = 0; i < nsplit_seq; ++i) {
-        const float mi = ld_cg_f32(ml + 2 * i);
-        const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
-        o += ld_cg_f32(p.ws_o + (row * p.num_splits + i) * D + d) * wi;
+  };
+  // issue at most one stage; the producer may run at most one unit ahead of the consumer
+  auto try_issue = [&]() -> bool {
+    for (;;) {
+      if (!P.valid) return false;
+      const int st = warp + pk * W;
+      if (pi >= 0 && st < P.nstages) {
+        const int blk0 = st * C::BPS;
+        const int nb = p_nblk - blk0 < C::BPS ? p_nblk - blk0 : C::BPS;
+        const int slot = n_issued % NST;
+        issue_stage_copies<C>(ring + slot * C::STAGE, bars + slot * 8, lane, phys_pref, nb, p_kbase, p_vbase,
+                              p.kv_block_stride);
+        ++n_issued;
+        ++pk;
+        const int st2 = warp + pk * W;
+        if (st2 < P.nstages) {
+          phys_pref = load_phys(st2);
+        } else if (pi <= ci) {
+          advance();  // share of this unit fully issued: step into the next unit right away
+        }
+        return true;
       }
-      p.out[row * D + d] = __float2half_rn(o * inv);
+      if (pi > ci) return false;  // already one unit ahead of the consumer
+      advance();
     }
+  };
+
+  advance();  // pi = 0
+  for (;;) {
+    // ---- consumer enters unit ci (the producer is in it too: pi == ci here) ----
+    while (pi < ci) advance();
+    const UnitDesc U = P;
+    if (!U.valid) break;
+    uint4 qv[C::NJ];
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) qv[j] = q_next[j];
+    if (lane == 0) mbar_arrive(uempty + (ci % kNU) * 8);  // this warp holds its own copy of the descriptor
+    while (n_issued - n_consumed < NST && try_issue()) {
+    }
+
+    float m = -INFINITY, lsum = 0.f;
+    float acc[C::NJ];
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) acc[j] = 0.f;
+
+    for (int st = warp; st < U.nstages; st += W) {
+      const int slot = n_consumed % NST;
+      mbar_wait(bars + slot * 8, (n_consumed / NST) & 1);
+      process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, m, lsum, acc, U.tok_begin + st * 32, U.tok_end,
+                       p.scale_log2e);
+      ++n_consumed;
+      try_issue();
+    }
+
+    float* red = red2 + (ci & 1) * (W * (D + 2));
+    warp_publish<C>(red, warp, lane, m, lsum, acc);
+    named_bar_sync<1, W * 32>();
+    cta_merge_and_store<C, W, 2>(p, red, threadIdx.x, U.seq, U.head, U.split, U.nsplit_seq, s_last);
+    ++ci;
   }
 }
 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
-constexpr int kCounterCap = 16384;  // int32 counters at the start of the workspace
+constexpr int kCounterCap = 16384;  // int32 words at the start of the workspace: [0..15] scheduler, rest split counters
+constexpr int kSchedWords = 16;
 
 struct Tuning {
   int force_splits = 0;
@@ -373,13 +622,18 @@ static Tuning g_tuning;
 
 struct Variant {
   int W, NST;
+  bool persistent;
 };
-// variant 0: 4 warps x 2 stages (64 KB/CTA at D=64 -> 3 CTAs/SM); 1: 4 x 3; 2: 8 x 1
-static constexpr Variant kVariants[] = {{4, 2}, {4, 3}, {8, 1}};
-constexpr int kNumVariants = 3;
+// 0 (default): classic grid (H, S, splits), 4 warps x 2 stages; 1: classic 4x3; 2: classic 8x1; 3: classic 2x2;
+// 4: persistent 4x2 (+1 scheduler warp); 5: persistent 8x1; 6: persistent 4x3; 7: persistent 2x2.
+// The persistent variants are kept for experiments: on B200 they measured 3-8 % SLOWER than the classic
+// grid at every BASELINE shape (profiles/r01c_persistent_vs_classic.md), so they are not the default.
+static constexpr Variant kVariants[] = {{4, 2, false}, {4, 3, false}, {8, 1, false}, {2, 2, false},
+                                        {4, 2, true},  {8, 1, true},  {4, 3, true},  {2, 2, true}};
+constexpr int kNumVariants = 8;
 
 template <int D, int B, int W, int NST>
-static int launch_one(const PaParams& p, int num_seqs, cudaStream_t stream) {
+static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
   using C = PaCfg<D, B, W, NST>;
   auto kern = pa_v1_kernel<D, B, W, NST>;
   static bool attr_set[64] = {};
@@ -396,28 +650,59 @@ static int launch_one(const PaParams& p, int num_seqs, cudaStream_t stream) {
   return VB200_OK;
 }
 
+template <int D, int B, int W, int NST>
+static int launch_persistent(const PaParams& p, int num_seqs, int* sched, cudaStream_t stream) {
+  using C = PaPersistCfg<D, B, W, NST>;
+  auto kern = pa_v1_persistent_kernel<D, B, W, NST>;
+  constexpr int kThreads = (W + 1) * 32;
+  static int resident[64] = {};  // CTAs that fit on the device at once (0 = not yet queried)
+  int dev = 0;
+  VB200_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return set_error(VB200_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", dev);
+  if (resident[dev] == 0) {
+    VB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    int per_sm = 0;
+    VB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, C::SMEM));
+    if (per_sm < 1) return set_error(VB200_ERR_CUDA, "persistent kernel does not fit on an SM");
+    resident[dev] = per_sm * device_sm_count();
+  }
+  const long long num_units = (long long)num_seqs * p.num_heads * p.num_splits;
+  if (num_units > 0x7fffffffLL - 65536) return set_error(VB200_ERR_INVALID_ARGUMENT, "too many work units");
+  const int grid = num_units < resident[dev] ? (int)num_units : resident[dev];
+  kern<<<grid, kThreads, C::SMEM, stream>>>(p, (int)num_units, sched);
+  count_launch();
+  VB200_CUDA_CHECK(cudaGetLastError());
+  return VB200_OK;
+}
+
 template <int D, int B>
-static int launch_variant(const PaParams& p, int num_seqs, int variant, cudaStream_t stream) {
+static int launch_variant(const PaParams& p, int num_seqs, int variant, int* sched, cudaStream_t stream) {
   switch (variant) {
-    case 1: return launch_one<D, B, 4, 3>(p, num_seqs, stream);
-    case 2: return launch_one<D, B, 8, 1>(p, num_seqs, stream);
-    default: return launch_one<D, B, 4, 2>(p, num_seqs, stream);
+    case 1: return launch_classic<D, B, 4, 3>(p, num_seqs, stream);
+    case 2: return launch_classic<D, B, 8, 1>(p, num_seqs, stream);
+    case 3: return launch_classic<D, B, 2, 2>(p, num_seqs, stream);
+    case 4: return launch_persistent<D, B, 4, 2>(p, num_seqs, sched, stream);
+    case 5: return launch_persistent<D, B, 8, 1>(p, num_seqs, sched, stream);
+    case 6: return launch_persistent<D, B, 4, 3>(p, num_seqs, sched, stream);
+    case 7: return launch_persistent<D, B, 2, 2>(p, num_seqs, sched, stream);
+    default: return launch_classic<D, B, 4, 2>(p, num_seqs, stream);
   }
 }
 
 template <int D>
-static int launch_block(const PaParams& p, int num_seqs, int block_size, int variant, cudaStream_t stream) {
+static int launch_block(const PaParams& p, int num_seqs, int block_size, int variant, int* sched,
+                        cudaStream_t stream) {
   switch (block_size) {
-    case 8: return launch_variant<D, 8>(p, num_seqs, variant, stream);
-    case 16: return launch_variant<D, 16>(p, num_seqs, variant, stream);
-    case 32: return launch_variant<D, 32>(p, num_seqs, variant, stream);
+    case 8: return launch_variant<D, 8>(p, num_seqs, variant, sched, stream);
+    case 16: return launch_variant<D, 16>(p, num_seqs, variant, sched, stream);
+    case 32: return launch_variant<D, 32>(p, num_seqs, variant, sched, stream);
     default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
   }
 }
 
 static int smem_bytes_for(int D, int variant) {
   const Variant v = kVariants[variant];
-  return v.W * v.NST * 128 * D + v.W * 64 + v.W * v.NST * 8 + v.W * (D + 2) * 4;
+  return v.W * v.NST * 128 * D + v.W * 64 + v.W * v.NST * 8 + (v.persistent ? 2 : 1) * v.W * (D + 2) * 4 + 256;
 }
 
 // split-KV factor: split only when (seq, head) pairs alone cannot fill ~2 waves of resident CTAs
@@ -430,10 +715,11 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
   const int64_t slots = (int64_t)num_sms * ctas_per_sm;
   const int64_t base = (int64_t)num_seqs * num_heads;
   const int quantum = 32 * v.W;  // tokens consumed by one round of the CTA's warps
+  const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
   if (g_tuning.force_splits > 0) {
     ns = g_tuning.force_splits;
-  } else if (base > 0 && base < 2 * slots && base <= kCounterCap) {
+  } else if (base > 0 && base < 2 * slots && base <= counter_cap) {
     ns = (int)((2 * slots + base - 1) / base);
     const int max_by_len = max_seq_len / (2 * quantum);  // >= 2 rounds per split
     if (ns > max_by_len) ns = max_by_len;
@@ -443,15 +729,19 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
   int st = max_seq_len > 0 ? (max_seq_len + ns - 1) / ns : quantum;
   st = (st + quantum - 1) / quantum * quantum;
   ns = max_seq_len > 0 ? (max_seq_len + st - 1) / st : 1;
-  if (base > kCounterCap) ns = 1;
+  if (base > counter_cap) ns = 1;
   *num_splits = ns < 1 ? 1 : ns;
   *split_tokens = st;
 }
 
+// workspace = [kCounterCap int32: scheduler words + split counters][ml: rows*2 f32][o: rows*D f32]
 static size_t workspace_bytes_for(int num_seqs, int num_heads, int head_size, int num_splits) {
-  if (num_splits <= 1) return 0;
-  const size_t rows = (size_t)num_seqs * num_heads * num_splits;
-  return (size_t)kCounterCap * 4 + rows * 2 * 4 + rows * head_size * 4;
+  size_t bytes = (size_t)kCounterCap * 4;  // tickets of the persistent scheduler live here even without split
+  if (num_splits > 1) {
+    const size_t rows = (size_t)num_seqs * num_heads * num_splits;
+    bytes += rows * 2 * 4 + rows * head_size * 4;
+  }
+  return bytes;
 }
 
 }  // namespace vb200
@@ -519,10 +809,12 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
   p.kv_head_stride = kv_head_stride;
   p.scale_log2e = (float)((double)scale * 1.4426950408889634074);
   int ns = 1, st = 0;
+  if (workspace != nullptr && (((uintptr_t)workspace & 15) || workspace_bytes < (size_t)kCounterCap * 4)) {
+    workspace = nullptr;  // unusable scratch: run without tickets and without split
+  }
   if (workspace != nullptr && max_seq_len > 0)
     choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), &ns, &st);
   if (ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
-  if (ns > 1 && ((uintptr_t)workspace & 15)) ns = 1;
   p.num_splits = ns;
   p.split_tokens = st;
   p.ws_cnt = nullptr;
@@ -530,13 +822,14 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
   p.ws_o = nullptr;
   if (ns > 1) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
-    p.ws_cnt = static_cast<int32_t*>(workspace);
+    p.ws_cnt = static_cast<int32_t*>(workspace) + kSchedWords;
     p.ws_ml = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (size_t)kCounterCap * 4);
     p.ws_o = p.ws_ml + rows * 2;
   }
+  int* sched = static_cast<int*>(workspace);  // nullptr => static round-robin unit assignment
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_size == 64) return launch_block<64>(p, num_seqs, block_size, variant, s);
-  return launch_block<128>(p, num_seqs, block_size, variant, s);
+  if (head_size == 64) return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
+  return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
 }
 
 extern "C" int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant) {
