@@ -32,6 +32,12 @@ CONFIGS = {
     "MIX": (256, 12, 64, 16, -2048),     # ctx ~ U[128, 2048] (BASELINE configs[2])
     "D128": (256, 8, 128, 16, 1024),
     "S1_8k": (1, 12, 64, 16, 8192),
+    "S1_1k": (1, 12, 64, 16, 1024),
+    "S4_4k": (4, 12, 64, 16, 4096),
+    "S16_512": (16, 12, 64, 16, 512),
+    "S32_1k": (32, 12, 64, 16, 1024),
+    "S128_256": (128, 12, 64, 16, 256),
+    "S128_1k": (128, 12, 64, 16, 1024),
     "S8_2k": (8, 12, 64, 16, 2048),
 }
 
