@@ -17,8 +17,8 @@ binding.  tokens/s = sequences advanced per step / step time.
             q/k/v, slot mappings, block tables, seq_lens and D2H of the attention output are inside
             the timed region (copies pipelined per layer on side streams)
   roofline  the dominant kernel (paged_attention_v1): algorithmic bytes per launch / mean launch
-            duration, measured with CUDA events around every attention launch INSIDE the timed
-            region, against the measured HBM peak in MEASURED_PEAKS.json
+            duration, measured with CUDA events around one attention launch per step (layer
+            step % 12) INSIDE the timed region, against the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline  the reference's CPU-runnable attention (torch eager, oracle/eager_attention.py)
             on the host cores over a bounded sample of the same tensors, rank 0, N=1 only
 
@@ -236,17 +236,20 @@ class DecodeHotPath:
         ops.paged_attention_v1(out[layer], q, self.key_cache, self.value_cache, H, self.scale,
                                block_tables[layer], seq_lens, B, CTX, None, "auto", 1.0, 0, 0, 1, 1, 0)
 
-    def step(self, ops, attn_events=None):
+    def step(self, ops, attn_events=None, probe_layer=-1):
+        """One decode step of the hot path.  If attn_events is given, the attention launch of layer
+        `probe_layer` is bracketed by CUDA events (one probe per step keeps the step itself undisturbed)."""
         torch = self.torch
         for l in range(LAYERS):
             q, k, v = self.views(self.qkv, l)
             ops.reshape_and_cache(k, v, self.key_cache, self.value_cache, self.slots[l], "auto", 1.0)
-            if attn_events is not None:
+            probe = attn_events is not None and l == probe_layer
+            if probe:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             ops.paged_attention_v1(self.out[l], q, self.key_cache, self.value_cache, H, self.scale,
                                    self.block_tables[l], self.seq_lens, B, CTX, None, "auto", 1.0, 0, 0, 1, 1, 0)
-            if attn_events is not None:
+            if probe:
                 e1.record()
                 attn_events.append((e0, e1))
 
@@ -413,8 +416,8 @@ def run_gpu_arm(args):
     sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for _ in range(args.steps):
-        hp.step(ops, attn_events)
+    for i in range(args.steps):
+        hp.step(ops, attn_events, probe_layer=i % LAYERS)
     t_end.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()

@@ -168,6 +168,39 @@ def test_strided_query_and_4d_out_like_vllmini():
     assert np.array_equal(out4.view(S, H, D).cpu().numpy().view(np.uint16), want.view(np.uint16))
 
 
+def test_ctypes_and_torch_shim_bindings_are_the_same_path():
+    """ops binds the C ABI either through the compiled torch shim or through ctypes; both must reach the
+    same kernels and give bit-identical results."""
+    from vllmini_b200 import _native, ops
+    c = build_case("ragged_small")
+    t = to_cuda(c)
+    S, H, D, B = c["S"], c["H"], c["D"], c["B"]
+    msl = int(t["bt"].shape[1]) * B
+    outs = []
+    for fn in (ops.paged_attention_v1, ops.paged_attention_v1_ctypes):
+        o = torch.zeros(S, H, D, dtype=torch.float16, device="cuda:0")
+        n0 = _native.launch_count()
+        fn(o, t["q"], t["kc"], t["vc"], H, c["scale"], t["bt"], t["sl"], B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+        torch.cuda.synchronize()
+        assert _native.launch_count() == n0 + 1
+        outs.append(o.cpu().numpy())
+    assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+    kcs = []
+    for fn in (ops.reshape_and_cache, ops.reshape_and_cache_ctypes):
+        kc, vc = torch.zeros_like(t["kc"]), torch.zeros_like(t["vc"])
+        k = torch.randn(7, H, D, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(3)).half()
+        fn(k, k, kc, vc, torch.arange(7, device="cuda:0") * 3, "auto", 1.0)
+        torch.cuda.synchronize()
+        kcs.append((kc.cpu(), vc.cpu()))
+    assert torch.equal(kcs[0][0], kcs[1][0]) and torch.equal(kcs[0][1], kcs[1][1])
+    with pytest.raises(RuntimeError, match="Unsupported block size"):
+        ops.paged_attention_v1(outs and torch.zeros(S, H, D, dtype=torch.float16, device="cuda:0"), t["q"], t["kc"], t["vc"],
+                               H, c["scale"], t["bt"], t["sl"], 4, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    with pytest.raises(RuntimeError, match="Int"):
+        ops.paged_attention_v1(torch.zeros(S, H, D, dtype=torch.float16, device="cuda:0"), t["q"], t["kc"], t["vc"],
+                               H, c["scale"], t["bt"].long(), t["sl"], B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+
+
 def test_garbage_beyond_seq_len_cannot_leak():
     c = build_case("block_plus_one")
     clean = run_cuda_attention(c)

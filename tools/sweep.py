@@ -62,7 +62,7 @@ def make(S, H, D, B, ctx, seed, dev, mixed=False):
     return q, kc, vc, bt, lens
 
 
-def time_config(name, variant, splits, iters=20, warm=5, ref=None):
+def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
     S, H, D, B, ctx = CONFIGS[name]
     mixed = ctx < 0
     ctx = abs(ctx)
@@ -81,20 +81,39 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None):
     for i in range(warm):
         call(i)
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for i in range(iters):
-        evs[i][0].record()
-        call(i)
-        evs[i][1].record()
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+    if graph:
+        # host launch overhead removed: `iters` back-to-back launches captured in one CUDA graph
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                call(i)
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / iters)
+        ts.sort()
+        del g
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i in range(iters):
+            evs[i][0].record()
+            call(i)
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
     med = ts[len(ts) // 2]
     ab = sum(algorithmic_bytes(S, H, D, B, p[4].tolist()) for p in pools) / npools
     _native.set_tuning(0, 0)
     del pools, outs
     torch.cuda.empty_cache()
     return dict(config=name, variant=variant, splits=splits, us_median=med, us_min=ts[0], gbps=ab / med / 1e3,
-                bytes=ab, impl="ref" if ref is not None else "new")
+                bytes=ab, impl="ref" if ref is not None else "new", timing="graph" if graph else "events")
 
 
 def main():
@@ -103,6 +122,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2")
     ap.add_argument("--splits", default="0")
     ap.add_argument("--ref", action="store_true", help="also time the reference's own kernel (oracle/_ref)")
+    ap.add_argument("--graph", action="store_true", help="time launches replayed from a CUDA graph (no host overhead)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     a = ap.parse_args()
     res = []
@@ -114,11 +134,11 @@ def main():
     for name in a.configs.split(","):
         for v in [int(x) for x in a.variants.split(",")]:
             for sp in [int(x) for x in a.splits.split(",")]:
-                r = time_config(name, v, sp)
+                r = time_config(name, v, sp, graph=a.graph)
                 res.append(r)
                 print(json.dumps(r), flush=True)
         if ref is not None:
-            r = time_config(name, 0, 0, ref=ref)
+            r = time_config(name, 0, 0, ref=ref, graph=a.graph)
             res.append(r)
             print(json.dumps(r), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)

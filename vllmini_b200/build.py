@@ -57,10 +57,46 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+SHIM_SRC = os.path.join(CSRC, "torch_shim.cpp")
+
+
+def shim_path() -> str:
+    import sysconfig
+    return os.path.join(PKG, "_torch_shim" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_shim(force: bool = False) -> str:
+    """Compile the torch-facing pybind11 shim (g++ only; links libvllmini_b200.so and torch).  It is an
+    optimisation of call overhead, not a different path: without it ops.py binds the same C ABI through
+    ctypes."""
+    out = shim_path()
+    deps = [SHIM_SRC, os.path.join(ROOT, "include", "vllmini_b200.h")]
+    if not force and os.path.isfile(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    import sysconfig
+
+    from torch.utils import cpp_extension as ce
+    build(force=False)
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-shared", "-fPIC", "-O2", "-std=c++17", "-w", SHIM_SRC, "-o", out + ".tmp",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-DTORCH_EXTENSION_NAME=_torch_shim", "-D_GLIBCXX_USE_CXX11_ABI=1",
+           "-I" + os.path.join(ROOT, "include"), "-I" + sysconfig.get_paths()["include"], "-I" + cuda_home + "/include"]
+    cmd += ["-I" + p for p in ce.include_paths()]
+    for l in ce.library_paths():
+        cmd += ["-L" + l, "-Wl,-rpath," + l]
+    cmd += ["-L" + LIB_DIR, "-Wl,-rpath,$ORIGIN/lib", "-lvllmini_b200", "-lc10", "-lc10_cuda", "-ltorch_cpu",
+            "-ltorch", "-ltorch_python"]
+    print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    os.replace(out + ".tmp", out)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose))
+    print(build_shim(force=a.force))
     sys.exit(0)

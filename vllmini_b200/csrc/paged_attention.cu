@@ -700,28 +700,22 @@ static int launch_block(const PaParams& p, int num_seqs, int block_size, int var
   }
 }
 
-static int smem_bytes_for(int D, int variant) {
-  const Variant v = kVariants[variant];
-  return v.W * v.NST * 128 * D + v.W * 64 + v.W * v.NST * 8 + (v.persistent ? 2 : 1) * v.W * (D + 2) * 4 + 256;
-}
-
-// split-KV factor: split only when (seq, head) pairs alone cannot fill ~2 waves of resident CTAs
+// split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
+// merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
+// is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
 static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq_len, int variant, int num_sms,
                          int* num_splits, int* split_tokens) {
+  (void)head_size;
   const Variant v = kVariants[variant];
-  const int smem = smem_bytes_for(head_size, variant) + 1024;
-  int ctas_per_sm = (227 * 1024) / smem;
-  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 16 ? 16 : ctas_per_sm);
-  const int64_t slots = (int64_t)num_sms * ctas_per_sm;
   const int64_t base = (int64_t)num_seqs * num_heads;
   const int quantum = 32 * v.W;  // tokens consumed by one round of the CTA's warps
   const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
   if (g_tuning.force_splits > 0) {
     ns = g_tuning.force_splits;
-  } else if (base > 0 && base < 2 * slots && base <= counter_cap) {
-    ns = (int)((2 * slots + base - 1) / base);
-    const int max_by_len = max_seq_len / (2 * quantum);  // >= 2 rounds per split
+  } else if (base > 0 && base <= num_sms) {
+    ns = (int)((2 * (int64_t)num_sms + base - 1) / base);
+    const int max_by_len = max_seq_len / 256;
     if (ns > max_by_len) ns = max_by_len;
     if (ns > 64) ns = 64;
   }

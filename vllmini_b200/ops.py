@@ -11,6 +11,7 @@ allocates nothing the caller can see, and returns None.
 """
 from __future__ import annotations
 
+import os as _os
 from typing import Dict, List, Optional
 
 import torch
@@ -76,7 +77,7 @@ def paged_attention_v1(
     [NB, KVH, D/8, B, 8]; value_cache [NB, KVH, D, B]; block_tables int32 [S, MB]; seq_lens int32 [S].
     """
     _require_cuda(query, "query")
-    if query.dtype != torch.float16:
+    if query.dtype is not torch.float16:
         # reference dispatch also has float/bfloat16 arms (quant_utils.cuh:529-566); vllmini is
         # fp16-only (kv_cache.py:13-14, scheduler.py:13) and so is this build
         raise RuntimeError(f"vllmini_b200: unsupported input type of kv cache: {query.dtype}")
@@ -90,11 +91,11 @@ def paged_attention_v1(
     for t, name in ((out, "out"), (key_cache, "key_cache"), (value_cache, "value_cache"),
                     (block_tables, "block_tables"), (seq_lens, "seq_lens")):
         _require_cuda(t, name)
-    if block_tables.dtype != torch.int32:
+    if block_tables.dtype is not torch.int32:
         raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {block_tables.dtype} (block_tables)")
-    if seq_lens.dtype != torch.int32:
+    if seq_lens.dtype is not torch.int32:
         raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {seq_lens.dtype} (seq_lens)")
-    if key_cache.dtype != torch.float16 or value_cache.dtype != torch.float16 or out.dtype != torch.float16:
+    if key_cache.dtype is not torch.float16 or value_cache.dtype is not torch.float16 or out.dtype is not torch.float16:
         raise RuntimeError("vllmini_b200: out, key_cache and value_cache must be float16")
     if query.dim() != 3 or query.stride(2) != 1 or query.stride(1) != query.size(2):
         raise RuntimeError("vllmini_b200: query must be [num_seqs, num_heads, head_size] with contiguous heads")
@@ -135,14 +136,14 @@ def reshape_and_cache(
     _require_cuda(key, "key")
     if kv_cache_dtype != "auto":
         raise RuntimeError(f"vllmini_b200: Unsupported data type of kv cache: {kv_cache_dtype}")
-    if key.dtype != torch.float16:
+    if key.dtype is not torch.float16:
         raise RuntimeError(f"vllmini_b200: unsupported input type of kv cache: {key.dtype}")
     for t, name in ((value, "value"), (key_cache, "key_cache"), (value_cache, "value_cache"),
                     (slot_mapping, "slot_mapping")):
         _require_cuda(t, name)
-    if slot_mapping.dtype != torch.int64:
+    if slot_mapping.dtype is not torch.int64:
         raise RuntimeError(f"vllmini_b200: expected scalar type Long but found {slot_mapping.dtype} (slot_mapping)")
-    if value.dtype != torch.float16 or key_cache.dtype != torch.float16 or value_cache.dtype != torch.float16:
+    if value.dtype is not torch.float16 or key_cache.dtype is not torch.float16 or value_cache.dtype is not torch.float16:
         raise RuntimeError("vllmini_b200: value, key_cache and value_cache must be float16")
     if key.dim() != 3 or key.stride(2) != 1 or key.stride(1) != key.size(2) \
             or value.stride(2) != 1 or value.stride(1) != value.size(2):
@@ -161,6 +162,25 @@ def reshape_and_cache(
         key.data_ptr(), value.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr(),
         num_tokens, num_heads, head_size, block_size, x, key.stride(0), value.stride(0), dev_index, stream)
     _check(rc)
+
+
+# ---- binding selection -------------------------------------------------------------------------------
+# The two functions above bind the C ABI through ctypes (no build dependency on torch).  When the compiled
+# torch shim (csrc/torch_shim.cpp -> _torch_shim*.so, `python -m vllmini_b200.build`) is present it replaces
+# them: same validation, same C ABI calls, same kernels, ~5x less Python overhead per call (the reference's
+# own binding is a pybind11 module too).  VLLMINI_B200_NO_SHIM=1 keeps the ctypes path.
+paged_attention_v1_ctypes = paged_attention_v1
+reshape_and_cache_ctypes = reshape_and_cache
+BINDING = "ctypes"
+if not _os.environ.get("VLLMINI_B200_NO_SHIM"):
+    try:
+        _native.load()                       # fail loudly first if the CUDA library itself is missing
+        from . import _torch_shim as _shim   # noqa: E402
+        paged_attention_v1 = _shim.paged_attention_v1
+        reshape_and_cache = _shim.reshape_and_cache
+        BINDING = "torch_shim"
+    except ImportError:
+        pass
 
 
 # ---- the rest of the reference's exported surface: present so `import` matches, but out of the
