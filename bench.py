@@ -255,28 +255,38 @@ class DecodeHotPath:
 
 
 class HostDrivenStep:
-    """The same step fed from pinned host memory: per layer, H2D of qkv / slot mapping / block
-    table (+ seq_lens once) on a copy stream, kernels on the compute stream, D2H of the layer's
-    attention output on a third stream; one host sync at the end of the step."""
+    """The same step fed from pinned host memory.  Per layer, ONE packed pinned buffer
+    [qkv fp16 | slot_mapping int64 | block_table int32] is copied H2D on a copy stream, the two kernels run
+    on the compute stream, and the layer's attention output is copied D2H on a third stream; the host
+    enqueues layer l+1's copy while the GPU runs layer l, and synchronises once per step."""
 
     def __init__(self, hp: DecodeHotPath):
         import torch
         self.torch, self.hp = torch, hp
         dev = hp.dev
-        self.h_qkv = hp.qkv.cpu().pin_memory()
-        self.h_slots = hp.slots.cpu().pin_memory()
-        self.h_bt = hp.block_tables.cpu().pin_memory()
+        self.n_qkv = S * 3 * H * D * 2
+        self.n_slots = S * 8
+        self.n_bt = S * hp.nblk * 4
+        self.stride = self.n_qkv + self.n_slots + self.n_bt
+        assert self.n_qkv % 16 == 0 and (self.n_qkv + self.n_slots) % 16 == 0
+        self.h_in = torch.empty((LAYERS, self.stride), dtype=torch.uint8).pin_memory()
+        self.d_in = torch.empty((LAYERS, self.stride), dtype=torch.uint8, device=dev)
+        for l in range(LAYERS):
+            self.h_in[l, : self.n_qkv].copy_(hp.qkv[l].cpu().view(torch.uint8).reshape(-1))
+            self.h_in[l, self.n_qkv: self.n_qkv + self.n_slots].copy_(hp.slots[l].cpu().view(torch.uint8).reshape(-1))
+            self.h_in[l, self.n_qkv + self.n_slots:].copy_(hp.block_tables[l].cpu().view(torch.uint8).reshape(-1))
         self.h_sl = hp.seq_lens.cpu().pin_memory()
-        self.h_out = torch.empty(hp.out.shape, dtype=torch.float16).pin_memory()
-        self.d_qkv = torch.empty_like(hp.qkv)
-        self.d_slots = torch.empty_like(hp.slots)
-        self.d_bt = torch.empty_like(hp.block_tables)
         self.d_sl = torch.empty_like(hp.seq_lens)
+        self.h_out = torch.empty(hp.out.shape, dtype=torch.float16).pin_memory()
         self.d_out = torch.empty_like(hp.out)
+        # typed device views of the packed staging buffer
+        self.d_qkv = [self.d_in[l, : self.n_qkv].view(torch.float16).view(S, 3 * H * D) for l in range(LAYERS)]
+        self.d_slots = [self.d_in[l, self.n_qkv: self.n_qkv + self.n_slots].view(torch.int64) for l in range(LAYERS)]
+        self.d_bt = [self.d_in[l, self.n_qkv + self.n_slots:].view(torch.int32).view(S, hp.nblk) for l in range(LAYERS)]
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.ev_in = [torch.cuda.Event() for _ in range(LAYERS)]
         self.ev_out = [torch.cuda.Event() for _ in range(LAYERS)]
-        self.h2d = (self.h_qkv.numel() * 2 + self.h_slots.numel() * 8 + self.h_bt.numel() * 4 + self.h_sl.numel() * 4)
+        self.h2d = self.h_in.numel() + self.h_sl.numel() * 4
         self.d2h = self.h_out.numel() * 2
 
     def step(self, ops):
@@ -285,14 +295,18 @@ class HostDrivenStep:
         self.s_in.wait_stream(cur)
         with torch.cuda.stream(self.s_in):
             self.d_sl.copy_(self.h_sl, non_blocking=True)
-            for l in range(LAYERS):
-                self.d_qkv[l].copy_(self.h_qkv[l], non_blocking=True)
-                self.d_slots[l].copy_(self.h_slots[l], non_blocking=True)
-                self.d_bt[l].copy_(self.h_bt[l], non_blocking=True)
-                self.ev_in[l].record(self.s_in)
         for l in range(LAYERS):
+            with torch.cuda.stream(self.s_in):
+                self.d_in[l].copy_(self.h_in[l], non_blocking=True)
+                self.ev_in[l].record(self.s_in)
             cur.wait_event(self.ev_in[l])
-            hp.layer(ops, l, self.d_qkv, self.d_slots, self.d_bt, self.d_sl, self.d_out)
+            qkv = self.d_qkv[l]
+            q = qkv[:, : H * D].view(S, H, D)
+            k = qkv[:, H * D: 2 * H * D].view(S, H, D)
+            v = qkv[:, 2 * H * D:].view(S, H, D)
+            ops.reshape_and_cache(k, v, hp.key_cache, hp.value_cache, self.d_slots[l], "auto", 1.0)
+            ops.paged_attention_v1(self.d_out[l], q, hp.key_cache, hp.value_cache, H, hp.scale, self.d_bt[l],
+                                   self.d_sl, B, CTX, None, "auto", 1.0, 0, 0, 1, 1, 0)
             self.ev_out[l].record(cur)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_out[l])
@@ -472,8 +486,9 @@ def run_gpu_arm(args):
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "how": "pinned host q/k/v+slots+block tables -> device, 24 launches, attention output -> "
-                           "pinned host, per-layer pipelining on 3 streams, host sync every step"},
+                    "how": "per layer one packed pinned buffer (q/k/v + slot mapping + block table) -> device, "
+                           "2 launches through the binding, attention output -> pinned host; copies pipelined "
+                           "against compute on 3 streams; host sync every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "vb200::pa_v1_kernel<64,16,4,2>", "achieved": achieved, "peak": peak,
