@@ -96,6 +96,28 @@ int vb200_reshape_and_cache_f16(const void* key, const void* value, void* key_ca
                                 int32_t head_size, int32_t block_size, int32_t x, int64_t key_stride,
                                 int64_t value_stride, int32_t device, void* stream);
 
+/*
+ * The rest of the reference's cache_ops surface (exported by paged_attention_cuda.cpp:57-60, not called by
+ * vllmini; pure copies, bit-exact):
+ *
+ * copy_blocks: for every layer and every (src, dst) pair of block_mapping [num_pairs, 2] (device, int64)
+ *   copy block src over block dst in that layer's key and value cache.  key_cache_ptrs / value_cache_ptrs
+ *   are DEVICE arrays of num_layers cache base addresses.  Replaces cache_kernels.cu:67-148.
+ * swap_blocks: one async copy per (src, dst) pair of block_mapping_host (HOST, int64) between two cache
+ *   tensors; kind 0 = device->device, 1 = device->host, 2 = host->device.  Replaces cache_kernels.cu:24-63.
+ * reshape_and_cache_flash: scatter rows into k_cache / v_cache laid out [num_blocks, block_size, num_heads,
+ *   head_size] (block_stride = k_cache.stride(0)).  Replaces cache_kernels.cu:209-240, 283-317.
+ */
+int vb200_copy_blocks(const int64_t* key_cache_ptrs, const int64_t* value_cache_ptrs, const int64_t* block_mapping,
+                      int32_t num_layers, int32_t num_pairs, int64_t block_bytes, int32_t all_16b_aligned,
+                      int32_t device, void* stream);
+int vb200_swap_blocks(const void* src, void* dst, const int64_t* block_mapping_host, int64_t num_pairs,
+                      int64_t block_bytes, int32_t kind, int32_t device, void* stream);
+int vb200_reshape_and_cache_flash_f16(const void* key, const void* value, void* k_cache, void* v_cache,
+                                      const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                                      int32_t head_size, int32_t block_size, int64_t block_stride, int64_t key_stride,
+                                      int64_t value_stride, int32_t device, void* stream);
+
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* vb200_last_error(void);
 

@@ -106,11 +106,17 @@ def test_shim_error_behaviour_mirrors_reference():
         ops.paged_attention_v1(torch.empty_like(q), q, kc, vc, 12, 0.125, bt, sl, 16, 64, *tail)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.reshape_and_cache(q, q, kc, vc, torch.zeros(1, dtype=torch.int64), "auto", 1.0)
-    # uncalled exports exist but are explicit about being out of scope
+    # the rest of the exported surface validates like the reference
+    with pytest.raises(RuntimeError, match="Invalid device combination"):       # cache_kernels.cu:37-39
+        ops.swap_blocks(q, q, torch.zeros(1, 2, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.copy_blocks([kc], [vc], torch.zeros(1, 2, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.reshape_and_cache_flash(q, q, kc, vc, torch.zeros(1, dtype=torch.int64), "auto")
+    with pytest.raises(RuntimeError, match="exp_sums"):
+        ops.paged_attention_v2(q, q, q, q, q, kc, vc, 12, 0.125, bt, sl, 16, 64, *tail)
     with pytest.raises(NotImplementedError):
-        ops.paged_attention_v2()
-    with pytest.raises(NotImplementedError):
-        ops.swap_blocks(q, q, bt)
+        ops.convert_fp8(kc, kc, 1.0, "auto")
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

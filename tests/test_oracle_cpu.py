@@ -168,3 +168,21 @@ def test_nan_garbage_beyond_seq_len_is_ignored():
     for mode in ("exact", "fp32", "ref_rounding"):
         g = c_oracle().paged_attention_v1(c["q"], kc, vc, c["scale"], c["bt"], c["sl"], mode=mode)
         assert np.isfinite(g.astype(np.float32)).all(), mode
+
+
+def test_uncalled_cache_ops_oracles():
+    rng = np.random.default_rng(0)
+    T, H, D, B, NB = 9, 2, 8, 4, 4
+    key = rng.standard_normal((T, H, D)).astype(np.float16)
+    val = rng.standard_normal((T, H, D)).astype(np.float16)
+    kc = np.zeros((NB, B, H, D), dtype=np.float16)
+    vc = np.zeros_like(kc)
+    slots = np.array([0, 1, 2, 3, 4, -1, 9, 15, 12], dtype=np.int64)
+    po.reshape_and_cache_flash(key, val, kc, vc, slots)
+    assert np.array_equal(kc[1, 0], key[4]) and np.array_equal(vc[3, 3], val[7]) and not kc[1, 1].any()
+    a, b = [kc.copy()], [vc.copy()]
+    po.copy_blocks(a, b, np.array([[0, 2], [3, 1]]))
+    assert np.array_equal(a[0][2], kc[0]) and np.array_equal(b[0][1], vc[3])
+    dst = np.zeros_like(kc)
+    po.swap_blocks(kc, dst, np.array([[1, 0]]))
+    assert np.array_equal(dst[0], kc[1]) and not dst[1].any()

@@ -376,3 +376,91 @@ def test_full_size_round_trip_reshape_then_attend():
     ops.paged_attention_v1(out, q, kc, vc, H, 0.125, bt, sl2, B, int(bt.shape[1]) * B, None, "auto", 1.0, 0, 0, 1, 1, 0)
     torch.cuda.synchronize()
     assert (out.float() - new_v.float()).abs().max().item() < 2e-2
+
+
+# ------------------------------------------------------------------------------ rest of the exported surface
+def test_paged_attention_v2_signature_gives_v1_result():
+    from vllmini_b200 import ops
+    c = build_case("ctx_mixed_long")
+    t = to_cuda(c)
+    S, H, D, B = c["S"], c["H"], c["D"], c["B"]
+    msl = int(t["bt"].shape[1]) * B
+    P = (msl + 511) // 512
+    out = torch.empty(S, H, D, dtype=torch.float16, device="cuda:0")
+    exp_sums = torch.empty(S, H, P, dtype=torch.float32, device="cuda:0")
+    max_logits = torch.empty_like(exp_sums)
+    tmp_out = torch.empty(S, H, P, D, dtype=torch.float16, device="cuda:0")
+    ops.paged_attention_v2(out, exp_sums, max_logits, tmp_out, t["q"], t["kc"], t["vc"], H, c["scale"], t["bt"], t["sl"],
+                           B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    torch.cuda.synchronize()
+    want = run_cuda_attention(c, t, max_seq_len=msl)
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), want.view(np.uint16))
+    truth = c_oracle().paged_attention_v1(c["q"], c["kc"], c["vc"], c["scale"], c["bt"], c["sl"], mode="exact")
+    assert_close_to_truth(out.cpu().numpy(), truth.astype(np.float64), what="v2")
+
+
+def test_reshape_and_cache_flash_bit_exact(ref_ext):
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(11)
+    T, H, D, B, NB = 53, 12, 64, 16, 6
+    qkv = rng.standard_normal((T, 3 * H * D)).astype(np.float16)
+    slots = rng.permutation(NB * B)[:T].astype(np.int64)
+    slots[7] = -1
+    dev = torch.device("cuda:0")
+    qkv_t = torch.from_numpy(qkv).to(dev)
+    k_t, v_t = qkv_t[:, H * D:2 * H * D].view(T, H, D), qkv_t[:, 2 * H * D:].view(T, H, D)
+    kc = torch.full((NB, B, H, D), 3.0, dtype=torch.float16, device=dev)
+    vc = torch.full((NB, B, H, D), 3.0, dtype=torch.float16, device=dev)
+    ops.reshape_and_cache_flash(k_t, v_t, kc, vc, torch.from_numpy(slots).to(dev), "auto")
+    torch.cuda.synchronize()
+    kc_w = np.full((NB, B, H, D), 3.0, dtype=np.float16)
+    vc_w = kc_w.copy()
+    po.reshape_and_cache_flash(qkv[:, H * D:2 * H * D].reshape(T, H, D), qkv[:, 2 * H * D:].reshape(T, H, D), kc_w, vc_w, slots)
+    assert np.array_equal(kc.cpu().numpy().view(np.uint16), kc_w.view(np.uint16))
+    assert np.array_equal(vc.cpu().numpy().view(np.uint16), vc_w.view(np.uint16))
+    if ref_ext is not None:      # and against the reference's own kernel
+        kc_r = torch.full((NB, B, H, D), 3.0, dtype=torch.float16, device=dev)
+        vc_r = torch.full((NB, B, H, D), 3.0, dtype=torch.float16, device=dev)
+        ref_ext.cache_ops.reshape_and_cache_flash(k_t, v_t, kc_r, vc_r, torch.from_numpy(slots).to(dev), "auto")
+        torch.cuda.synchronize()
+        assert torch.equal(kc_r, kc) and torch.equal(vc_r, vc)
+
+
+def test_copy_blocks_and_swap_blocks_bit_exact(ref_ext):
+    from vllmini_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    L, NB, H, D, B = 3, 10, 4, 64, 16
+    kcs = [torch.randn(NB, H, D // 8, B, 8, generator=g, device=dev).half() for _ in range(L)]
+    vcs = [torch.randn(NB, H, D, B, generator=g, device=dev).half() for _ in range(L)]
+    mapping = torch.tensor([[0, 5], [1, 6], [2, 9]], dtype=torch.int64)
+    k_np = [k.cpu().numpy().copy() for k in kcs]
+    v_np = [v.cpu().numpy().copy() for v in vcs]
+    po.copy_blocks(k_np, v_np, mapping.numpy())
+    if ref_ext is not None:
+        kr, vr = [k.clone() for k in kcs], [v.clone() for v in vcs]
+        ref_ext.cache_ops.copy_blocks(kr, vr, mapping.to(dev))
+    ops.copy_blocks(kcs, vcs, mapping.to(dev))
+    torch.cuda.synchronize()
+    for l in range(L):
+        assert np.array_equal(kcs[l].cpu().numpy().view(np.uint16), k_np[l].view(np.uint16))
+        assert np.array_equal(vcs[l].cpu().numpy().view(np.uint16), v_np[l].view(np.uint16))
+        if ref_ext is not None:
+            assert torch.equal(kr[l], kcs[l]) and torch.equal(vr[l], vcs[l])
+    # swap: GPU -> CPU, CPU -> GPU, GPU -> GPU
+    src = kcs[0]
+    host = torch.zeros(NB, H, D // 8, B, 8, dtype=torch.float16).pin_memory()
+    ops.swap_blocks(src, host, torch.tensor([[3, 0], [4, 7]], dtype=torch.int64))
+    torch.cuda.synchronize()
+    assert torch.equal(host[0], src[3].cpu()) and torch.equal(host[7], src[4].cpu()) and not host[1].any()
+    back = torch.zeros_like(src)
+    ops.swap_blocks(host, back, torch.tensor([[0, 2], [7, 1]], dtype=torch.int64))
+    other = torch.zeros_like(src)
+    ops.swap_blocks(src, other, torch.tensor([[9, 9]], dtype=torch.int64))
+    torch.cuda.synchronize()
+    assert torch.equal(back[2], src[3]) and torch.equal(back[1], src[4]) and torch.equal(other[9], src[9])
+    if ref_ext is not None:
+        host_r = torch.zeros(NB, H, D // 8, B, 8, dtype=torch.float16).pin_memory()
+        ref_ext.cache_ops.swap_blocks(src, host_r, torch.tensor([[3, 0], [4, 7]], dtype=torch.int64))
+        torch.cuda.synchronize()
+        assert torch.equal(host_r, host)

@@ -183,26 +183,138 @@ if not _os.environ.get("VLLMINI_B200_NO_SHIM"):
         pass
 
 
-# ---- the rest of the reference's exported surface: present so `import` matches, but out of the
-#      hot path (no vllmini caller) ----
-def paged_attention_v2(*args, **kwargs) -> None:
-    raise NotImplementedError("paged_attention_v2 is exported by the reference (paged_attention_cuda.cpp:27-48) "
-                              "but never called by vllmini; paged_attention_v1 here already splits long contexts")
+# ---- the rest of the reference's exported surface -------------------------------------------------
+# Present so that the drop-in covers what the reference package exports (paged_attention_cuda.cpp:51-61).
+# vllmini calls none of these; they are control-plane
+# operations, so they stay on the ctypes binding.
+def paged_attention_v2(
+    out: torch.Tensor,
+    exp_sums: torch.Tensor,
+    max_logits: torch.Tensor,
+    tmp_out: torch.Tensor,
+    query: torch.Tensor,
+    key_cache: torch.Tensor,
+    value_cache: torch.Tensor,
+    num_kv_heads: int,
+    scale: float,
+    block_tables: torch.Tensor,
+    seq_lens: torch.Tensor,
+    block_size: int,
+    max_seq_len: int,
+    alibi_slopes: Optional[torch.Tensor],
+    kv_cache_dtype: str,
+    kv_scale: float,
+    tp_rank: int = 0,
+    blocksparse_local_blocks: int = 0,
+    blocksparse_vert_stride: int = 1,
+    blocksparse_block_size: int = 1,
+    blocksparse_head_sliding_step: int = 0,
+) -> None:
+    """The reference's split-KV entry (attention_kernels.cu:966-990; 512-token partitions + a reduce
+    kernel, :564-669).  Same result as paged_attention_v1; the B200 kernel already splits long contexts
+    inside v1 (with its own fp32 workspace and an in-kernel merge), so v2 validates the caller's scratch
+    tensors -- exp_sums / max_logits [S, H, P], tmp_out [S, H, P, D], P = ceil(max_seq_len / 512) -- and
+    runs the v1 path; the scratch tensors are left untouched."""
+    S, H, D = query.shape
+    P = (int(max_seq_len) + 511) // 512
+    if tuple(exp_sums.shape) != (S, H, P) or tuple(max_logits.shape) != (S, H, P):
+        raise RuntimeError(f"vllmini_b200: exp_sums/max_logits must be [{S}, {H}, {P}]")
+    if tuple(tmp_out.shape) != (S, H, P, D):
+        raise RuntimeError(f"vllmini_b200: tmp_out must be [{S}, {H}, {P}, {D}]")
+    if exp_sums.dtype is not torch.float32 or max_logits.dtype is not torch.float32:
+        raise RuntimeError("vllmini_b200: exp_sums and max_logits must be float32")
+    paged_attention_v1(out, query, key_cache, value_cache, num_kv_heads, scale, block_tables, seq_lens,
+                       block_size, max_seq_len, alibi_slopes, kv_cache_dtype, kv_scale, tp_rank,
+                       blocksparse_local_blocks, blocksparse_vert_stride, blocksparse_block_size,
+                       blocksparse_head_sliding_step)
 
 
 def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: torch.Tensor) -> None:
-    raise NotImplementedError("cache_ops.swap_blocks (cache_kernels.cu:24-63) has no vllmini caller")
+    """Copy whole cache blocks between two cache tensors (GPU<->GPU, GPU->CPU, CPU->GPU) for every
+    (src_block, dst_block) row of the CPU int64 `block_mapping`.  Reference: cache_kernels.cu:24-63."""
+    if src.is_cuda and dst.is_cuda:
+        if src.device != dst.device:
+            raise RuntimeError("vllmini_b200: src and dst must be on the same GPU")
+        kind, dev = 0, src.device
+    elif src.is_cuda and not dst.is_cuda:
+        kind, dev = 1, src.device
+    elif not src.is_cuda and dst.is_cuda:
+        kind, dev = 2, dst.device
+    else:
+        raise RuntimeError("vllmini_b200: Invalid device combination")
+    if block_mapping.is_cuda:
+        raise RuntimeError("vllmini_b200: block_mapping must be on CPU")
+    if not src.is_contiguous() or not dst.is_contiguous():
+        raise RuntimeError("vllmini_b200: src and dst must be contiguous")
+    bm = block_mapping.to(torch.int64).contiguous()
+    block_bytes = src.element_size() * src[0].numel()
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    rc = lib.vb200_swap_blocks(src.data_ptr(), dst.data_ptr(), bm.data_ptr(), bm.size(0), block_bytes, kind,
+                               dev_index, torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
 
 
 def copy_blocks(key_caches: List[torch.Tensor], value_caches: List[torch.Tensor],
                 block_mapping: torch.Tensor) -> None:
-    raise NotImplementedError("cache_ops.copy_blocks (cache_kernels.cu:96-148) has no vllmini caller")
+    """For every layer, copy block src over block dst in that layer's key and value cache, for every
+    (src, dst) row of the CUDA int64 `block_mapping` [num_pairs, 2].  Reference: cache_kernels.cu:67-148."""
+    num_layers = len(key_caches)
+    if num_layers != len(value_caches):
+        raise RuntimeError("vllmini_b200: key_caches and value_caches must have the same length")
+    if num_layers == 0:
+        return
+    dev = key_caches[0].device
+    if not dev.type == "cuda":
+        raise RuntimeError("vllmini_b200: caches must be CUDA tensors")
+    if not block_mapping.is_cuda or block_mapping.dtype is not torch.int64:
+        raise RuntimeError("vllmini_b200: block_mapping must be a CUDA int64 tensor")
+    bm = block_mapping.contiguous()
+    ptrs = [t.data_ptr() for t in key_caches] + [t.data_ptr() for t in value_caches]
+    # like the reference, the pointer table is staged through a small H2D copy (cache_kernels.cu:121-130)
+    table = torch.tensor(ptrs, dtype=torch.int64).to(dev, non_blocking=False)
+    block_bytes = key_caches[0].element_size() * key_caches[0][0].numel()
+    aligned = int(all(p % 16 == 0 for p in ptrs))
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    rc = lib.vb200_copy_blocks(table.data_ptr(), table.data_ptr() + 8 * num_layers, bm.data_ptr(), num_layers,
+                               bm.size(0), block_bytes, aligned, dev_index,
+                               torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
 
 
-def reshape_and_cache_flash(*args, **kwargs) -> None:
-    raise NotImplementedError("cache_ops.reshape_and_cache_flash (cache_kernels.cu:283-317) has no vllmini caller")
+def reshape_and_cache_flash(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                            slot_mapping: torch.Tensor, kv_cache_dtype: str) -> None:
+    """Scatter key/value rows [T, H, D] into caches laid out [num_blocks, block_size, H, D].
+    Reference: cache_kernels.cu:283-317 (entry), :209-240 (kernel)."""
+    _require_cuda(key, "key")
+    if kv_cache_dtype != "auto":
+        raise RuntimeError(f"vllmini_b200: Unsupported data type of kv cache: {kv_cache_dtype}")
+    for t, name in ((value, "value"), (k_cache, "k_cache"), (v_cache, "v_cache"), (slot_mapping, "slot_mapping")):
+        _require_cuda(t, name)
+    if key.dtype is not torch.float16 or value.dtype is not torch.float16 or k_cache.dtype is not torch.float16 \
+            or v_cache.dtype is not torch.float16:
+        raise RuntimeError("vllmini_b200: key, value and caches must be float16")
+    if slot_mapping.dtype is not torch.int64:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Long but found {slot_mapping.dtype} (slot_mapping)")
+    if k_cache.stride(0) != v_cache.stride(0):
+        raise RuntimeError("vllmini_b200: k_cache.stride(0) must equal v_cache.stride(0)")   # cache_kernels.cu:300
+    T, H, D = key.shape
+    if key.stride(2) != 1 or key.stride(1) != D or value.stride(2) != 1 or value.stride(1) != D:
+        raise RuntimeError("vllmini_b200: key/value must have contiguous heads")
+    if tuple(k_cache.shape[2:]) != (H, D) or k_cache.stride(3) != 1 or k_cache.stride(2) != D \
+            or k_cache.stride(1) != H * D:
+        raise RuntimeError("vllmini_b200: k_cache must be [num_blocks, block_size, num_heads, head_size]")
+    dev = key.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    rc = lib.vb200_reshape_and_cache_flash_f16(key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                                               slot_mapping.contiguous().data_ptr(), T, H, D, k_cache.size(1),
+                                               k_cache.stride(0), key.stride(0), value.stride(0), dev_index,
+                                               torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
 
 
 def convert_fp8(*args, **kwargs) -> None:
     raise NotImplementedError("cache_ops.convert_fp8 (cache_kernels.cu:334-392) is test-only and fp8 is disabled "
-                              "in the reference build (no ENABLE_FP8)")
+                              "in the reference build (no ENABLE_FP8: its kernel body is assert(false))")
