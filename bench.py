@@ -440,6 +440,24 @@ def run_gpu_arm(args):
     ms_total = t_start.elapsed_time(t_end)
     attn_us = [a.elapsed_time(b) * 1e3 for a, b in attn_events]
 
+    # ---- context row: the same step with the fused append+attend launch (12 launches instead of 24) ----
+    def fused_step():
+        for l in range(LAYERS):
+            q, k, v = hp.views(hp.qkv, l)
+            ops.paged_attention_v1_append(hp.out[l], q, k, v, hp.key_cache, hp.value_cache, hp.slots[l], H, hp.scale,
+                                          hp.block_tables[l], hp.seq_lens, B, CTX)
+    for _ in range(3):
+        fused_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fused_step()
+    f1.record()
+    torch.cuda.synchronize()
+    fused_ms = f0.elapsed_time(f1)
+    barrier()
+
     # ---- timed region 2: host-driven (e2e) ----
     hd = HostDrivenStep(hp)
     for _ in range(warm):
@@ -453,7 +471,7 @@ def run_gpu_arm(args):
     barrier()
 
     from vllmini_b200 import sharding
-    ms_total, e2e_s = sharding.reduce_max([ms_total, e2e_s], dev)      # the job is as slow as its slowest rank
+    ms_total, e2e_s, fused_ms = sharding.reduce_max([ms_total, e2e_s, fused_ms], dev)   # slowest rank sets the pace
 
     full_model = None
     h2d_bytes, d2h_bytes = hd.h2d, hd.d2h
@@ -499,6 +517,10 @@ def run_gpu_arm(args):
                          "launches_timed": len(attn_us), "attention_share_of_step": attn_mean_us * LAYERS / (ms_step * 1e3),
                          "traffic": recorded_traffic()},
         }
+        line["fused_step"] = {"value": world * S / (fused_ms / args.steps * 1e-3), "unit": "tokens/s",
+                              "ms_per_step": fused_ms / args.steps,
+                              "how": "same workload with vb200_paged_attention_v1_append_f16: scatter + attention in "
+                                     "one launch per layer (12 launches/step); extension beyond the reference API"}
         if full_model is not None:
             line["full_model"] = full_model
         if world == 1 and not args.no_cpu_baseline:

@@ -78,6 +78,23 @@ int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_c
                                  int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
                                  size_t workspace_bytes, int32_t device, void* stream);
 
+/*
+ * Fused decode step of one layer (no reference counterpart -- the reference
+ * always issues the two calls separately, gpt2.py:44,62): exactly reshape_and_cache(key, value, ...,
+ * slot_mapping) followed by paged_attention_v1(...), in ONE launch.  key / value [num_seqs, num_kv_heads,
+ * head_size]: one new token per sequence (decode), row strides key_stride / value_stride.  The token of
+ * sequence s must sit at position >= seq_lens[s] - 1 of that sequence (seq_lens[s] - 1 if it attends to
+ * itself; seq_lens[s] with the reference scheduler's convention).  slot_mapping[s] < 0 skips the write.
+ */
+int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
+                                        void* key_cache, void* value_cache, const int64_t* slot_mapping,
+                                        const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
+                                        int32_t num_heads, int32_t num_kv_heads, int32_t head_size,
+                                        int32_t block_size, int32_t max_num_blocks_per_seq, int32_t max_seq_len,
+                                        int64_t q_stride, int64_t key_stride, int64_t value_stride,
+                                        int64_t kv_block_stride, int64_t kv_head_stride, float scale,
+                                        void* workspace, size_t workspace_bytes, int32_t device, void* stream);
+
 /* Bytes of workspace that lets the launcher use dynamic unit scheduling (64 KiB of ticket / counter
  * words, always) and its preferred split-KV factor for this problem shape (partials, when it splits). */
 size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,

@@ -18,9 +18,9 @@ def _load(name):
     return g, GPT2Shape(n_layer=L, n_head=H, n_embd=E, vocab_size=V, n_positions=P)
 
 
-def _run(shape, seed, prompts, new_tokens, use_graph, max_seqs=None, dtype=torch.float16):
+def _run(shape, seed, prompts, new_tokens, use_graph, max_seqs=None, dtype=torch.float16, fused=True):
     dev = torch.device("cuda:0")
-    model = GPT2Decoder(shape, dev, dtype=dtype)
+    model = GPT2Decoder(shape, dev, dtype=dtype, fused_append=fused)
     model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=seed))
     B, MB = 16, 4
     S = max_seqs or len(prompts)
@@ -64,7 +64,8 @@ def test_greedy_decode_matches_reference_model_golden(name, use_graph, batched):
     prompts = [prompt]
     if batched:      # other sequences of different lengths in the same batch must not change row 0
         prompts += [rng.integers(0, shape.vocab_size, size=n).tolist() for n in (3, 16, 17, 30)]
-    toks, rows = _run(shape, int(g["seed"]), prompts, len(g["tokens"]), use_graph, max_seqs=len(prompts) + 1)
+    toks, rows = _run(shape, int(g["seed"]), prompts, len(g["tokens"]), use_graph, max_seqs=len(prompts) + 1,
+                      fused=use_graph)      # graph runs use the fused append+attend launch, eager runs the two calls
     tol = 0.06       # fp16 weights/activations vs the reference model in fp32 on CPU
     for step, row in enumerate(rows):
         want_v, want_i = g["top_vals"][step], g["top_ids"][step]

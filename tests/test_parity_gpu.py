@@ -464,3 +464,50 @@ def test_copy_blocks_and_swap_blocks_bit_exact(ref_ext):
         ref_ext.cache_ops.swap_blocks(src, host_r, torch.tensor([[3, 0], [4, 7]], dtype=torch.int64))
         torch.cuda.synchronize()
         assert torch.equal(host_r, host)
+
+
+# ------------------------------------------------------------------------------ fused append + attend
+@pytest.mark.parametrize("self_attend", [True, False])
+@pytest.mark.parametrize("shape", ["batch", "long_small_batch", "gqa"])
+def test_fused_append_equals_reshape_then_attention(self_attend, shape):
+    """vb200_paged_attention_v1_append_f16 == reshape_and_cache followed by paged_attention_v1, bit for bit
+    (same kernel arithmetic), for both position conventions: the new token attends to itself
+    (seq_len counts it) or not (the reference scheduler's off-by-one, scheduler.py:96-101)."""
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(17)
+    if shape == "batch":
+        S, H, KVH, D, B = 37, 12, 12, 64, 16
+        hist = rng.integers(0, 200, size=S)                 # tokens already cached (0 = brand-new sequence)
+    elif shape == "long_small_batch":
+        S, H, KVH, D, B = 2, 12, 12, 64, 16                 # split-KV path
+        hist = np.array([3000, 2047])
+    else:
+        S, H, KVH, D, B = 5, 8, 2, 128, 32
+        hist = np.array([0, 31, 32, 33, 100])
+    lens_after = hist + 1
+    q, kc, vc, bt, _ = po.make_case(S, KVH, D, B, lens_after, seed=23, max_blocks_per_seq=int(lens_after.max() // B + 2))
+    q = rng.standard_normal((S, H, D)).astype(np.float16)
+    dev = torch.device("cuda:0")
+    new_qkv = torch.from_numpy(rng.standard_normal((S, (H + 2 * KVH) * D)).astype(np.float16)).to(dev)
+    k_new = new_qkv[:, H * D:(H + KVH) * D].view(S, KVH, D)          # strided views like gpt2.py:36-41
+    v_new = new_qkv[:, (H + KVH) * D:].view(S, KVH, D)
+    slots = torch.from_numpy(bt[np.arange(S), hist // B].astype(np.int64) * B + hist % B).to(dev)
+    seq_lens = torch.from_numpy((lens_after if self_attend else hist).astype(np.int32)).to(dev)
+    bt_t, q_t = torch.from_numpy(bt).to(dev), torch.from_numpy(q).to(dev)
+    msl = int(bt.shape[1]) * B
+
+    kc_a, vc_a = torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev)
+    out_a = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+    ops.reshape_and_cache(k_new, v_new, kc_a, vc_a, slots, "auto", 1.0)
+    ops.paged_attention_v1(out_a, q_t, kc_a, vc_a, KVH, 0.1, bt_t, seq_lens, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+
+    kc_b, vc_b = torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev)
+    out_b = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+    ops.paged_attention_v1_append(out_b, q_t, k_new, v_new, kc_b, vc_b, slots, KVH, 0.1, bt_t, seq_lens, B, msl)
+    torch.cuda.synchronize()
+    assert torch.equal(kc_a, kc_b) and torch.equal(vc_a, vc_b), "fused scatter differs from reshape_and_cache"
+    assert torch.equal(out_a, out_b), "fused attention differs from the two-launch result"
+    # and both agree with the oracle run on the updated cache
+    truth = po.paged_attention_v1_exact(q, kc_a.cpu().numpy(), vc_a.cpu().numpy(), 0.1, bt, seq_lens.cpu().numpy(),
+                                        num_kv_heads=KVH)
+    assert_close_to_truth(out_b.cpu().numpy(), truth, what="fused append")

@@ -19,6 +19,9 @@ _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ct
 SYMBOLS = {
     "vb200_paged_attention_v1_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                             _i64, _i64, _i64, _f32, _vp, _sz, _i32, _vp]),
+    "vb200_paged_attention_v1_append_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                                   _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _sz,
+                                                   _i32, _vp]),
     "vb200_paged_attention_v1_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "vb200_reshape_and_cache_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                            _i32, _vp]),

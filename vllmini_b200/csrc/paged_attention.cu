@@ -51,6 +51,15 @@ struct PaParams {
   int32_t* ws_cnt;   // [num_seqs * num_heads] zero between launches
   float* ws_ml;      // [num_seqs * num_heads * num_splits * 2]
   float* ws_o;       // [num_seqs * num_heads * num_splits * D]
+  // fused append (vb200_paged_attention_v1_append_f16): this step's K/V rows [num_seqs, num_kv_heads, D] are
+  // scattered into the caches by the CTA that attends over the new token.  new_k == nullptr: plain v1.
+  const __half* __restrict__ new_k;
+  const __half* __restrict__ new_v;
+  const int64_t* __restrict__ slot_mapping;
+  int64_t new_k_stride;
+  int64_t new_v_stride;
+  __half* kc_w;
+  __half* vc_w;
 };
 
 template <int D, int B, int W, int NST>
@@ -353,6 +362,26 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
 #pragma unroll
     for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + C::BAR_OFF) + i * 8, 1);
     fence_mbar_init();
+  }
+  // ---- fused append: the CTA of the LAST live split of (seq, head) first writes this step's K/V row of its
+  //      kv head into the caches -- the same element moves as reshape_and_cache (cache_kernels.cu:178-199) --
+  //      then fences generic -> async proxy so that its own bulk copies read the new row.  Contract: the new
+  //      token sits at position >= seq_len - 1 (seq_len - 1 when it attends to itself, seq_len with the
+  //      reference scheduler's convention), so no other split reads that slot. ----
+  if (p.new_k != nullptr && split == r.nsplit_seq - 1) {
+    const int64_t slot = p.slot_mapping[seq];
+    if (slot >= 0) {
+      const int64_t blk = slot / B;
+      const int off = (int)(slot % B);
+      __half* kdst = p.kc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
+      __half* vdst = p.vc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
+      const __half* ksrc = p.new_k + (int64_t)seq * p.new_k_stride + (int64_t)kv_head * D;
+      const __half* vsrc = p.new_v + (int64_t)seq * p.new_v_stride + (int64_t)kv_head * D;
+      for (int i = threadIdx.x; i < D / 8; i += W * 32)
+        *reinterpret_cast<uint4*>(kdst + ((int64_t)i * B + off) * 8) = ldg128(ksrc + i * 8);
+      for (int i = threadIdx.x; i < D; i += W * 32) vdst[(int64_t)i * B + off] = vsrc[i];
+      fence_proxy_async_global();
+    }
   }
   __syncthreads();
 
@@ -753,13 +782,21 @@ extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int
   return workspace_bytes_for(num_seqs, num_heads, head_size, ns);
 }
 
-extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache,
-                                            const void* value_cache, const int32_t* block_tables,
-                                            const int32_t* seq_lens, int32_t num_seqs, int32_t num_heads,
-                                            int32_t num_kv_heads, int32_t head_size, int32_t block_size,
-                                            int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
-                                            int64_t kv_block_stride, int64_t kv_head_stride, float scale,
-                                            void* workspace, size_t workspace_bytes, int32_t device, void* stream) {
+namespace {
+struct AppendArgs {
+  const void* new_k = nullptr;
+  const void* new_v = nullptr;
+  const int64_t* slot_mapping = nullptr;
+  int64_t new_k_stride = 0, new_v_stride = 0;
+};
+}  // namespace
+
+static int paged_attention_impl(void* out, const void* query, const void* key_cache, const void* value_cache,
+                                const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
+                                int32_t num_heads, int32_t num_kv_heads, int32_t head_size, int32_t block_size,
+                                int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
+                                int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
+                                size_t workspace_bytes, int32_t device, void* stream, const AppendArgs& a) {
   if (num_seqs < 0 || num_heads <= 0 || num_kv_heads <= 0 || max_num_blocks_per_seq < 0)
     return set_error(VB200_ERR_INVALID_ARGUMENT, "negative or zero size argument");
   if (block_size != 8 && block_size != 16 && block_size != 32)
@@ -814,6 +851,14 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
   p.ws_cnt = nullptr;
   p.ws_ml = nullptr;
   p.ws_o = nullptr;
+  p.new_k = static_cast<const __half*>(a.new_k);
+  p.new_v = static_cast<const __half*>(a.new_v);
+  p.slot_mapping = a.slot_mapping;
+  p.new_k_stride = a.new_k_stride;
+  p.new_v_stride = a.new_v_stride;
+  p.kc_w = static_cast<__half*>(const_cast<void*>(key_cache));
+  p.vc_w = static_cast<__half*>(const_cast<void*>(value_cache));
+  if (a.new_k != nullptr && kVariants[variant].persistent) variant = 0;  // the fused append lives in the classic kernel
   if (ns > 1) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
     p.ws_cnt = static_cast<int32_t*>(workspace) + kSchedWords;
@@ -824,6 +869,44 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (head_size == 64) return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
   return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
+}
+
+extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache,
+                                            const void* value_cache, const int32_t* block_tables,
+                                            const int32_t* seq_lens, int32_t num_seqs, int32_t num_heads,
+                                            int32_t num_kv_heads, int32_t head_size, int32_t block_size,
+                                            int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
+                                            int64_t kv_block_stride, int64_t kv_head_stride, float scale,
+                                            void* workspace, size_t workspace_bytes, int32_t device, void* stream) {
+  return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
+                              num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
+                              kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream,
+                              AppendArgs{});
+}
+
+extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
+                                                   void* key_cache, void* value_cache, const int64_t* slot_mapping,
+                                                   const int32_t* block_tables, const int32_t* seq_lens,
+                                                   int32_t num_seqs, int32_t num_heads, int32_t num_kv_heads,
+                                                   int32_t head_size, int32_t block_size,
+                                                   int32_t max_num_blocks_per_seq, int32_t max_seq_len,
+                                                   int64_t q_stride, int64_t key_stride, int64_t value_stride,
+                                                   int64_t kv_block_stride, int64_t kv_head_stride, float scale,
+                                                   void* workspace, size_t workspace_bytes, int32_t device,
+                                                   void* stream) {
+  if (num_seqs > 0 && (!key || !value || !slot_mapping))
+    return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
+  if ((((uintptr_t)key | (uintptr_t)value) & 15) || (key_stride % 8) || (value_stride % 8))
+    return set_error(VB200_ERR_INVALID_ARGUMENT, "key/value rows must be 16-byte aligned");
+  AppendArgs a;
+  a.new_k = key;
+  a.new_v = value;
+  a.slot_mapping = slot_mapping;
+  a.new_k_stride = key_stride;
+  a.new_v_stride = value_stride;
+  return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
+                              num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
+                              kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream, a);
 }
 
 extern "C" int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant) {

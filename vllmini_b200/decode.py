@@ -195,8 +195,10 @@ class GPT2Decoder:
     Parameter names and shapes are the reference GPT2LMHeadModel's (nn.Linear [out, in] weights,
     exact-erf GELU as gpt2.py:123), so `load_state_dict` accepts a reference state_dict."""
 
-    def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16):
+    def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16, fused_append: bool = True):
         self.shape, self.device, self.dtype = shape, device, dtype
+        # decode: one fused launch per layer (scatter + attention) instead of the reference's two calls
+        self.fused_append = fused_append
         self.w: Dict[str, torch.Tensor] = {}
         self.scale = shape.head_size ** -0.5
         self._graph = None
@@ -264,10 +266,14 @@ class GPT2Decoder:
             p = f"transformer.h.{i}."
             qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
             q, k, v = (t.view(S, H, D) for t in qkv.split(s.n_embd, dim=-1))
-            ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], "auto", 1.0)
             o = torch.empty((S, H, D), dtype=self.dtype, device=self.device)
-            ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[i], kv.d_lens,
-                                   B, max_seq_len, None, "auto", 1.0, 0, 0, 1, 1, 0)
+            if self.fused_append:
+                ops.paged_attention_v1_append(o, q, k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], H, self.scale,
+                                              kv.d_tables[i], kv.d_lens, B, max_seq_len)
+            else:
+                ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], "auto", 1.0)
+                ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[i], kv.d_lens,
+                                       B, max_seq_len, None, "auto", 1.0, 0, 0, 1, 1, 0)
             x = x + F.linear(o.view(S, s.n_embd), self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
             x = x + self._mlp(self._ln(x, p + "ln_2"), p)
         return F.linear(self._ln(x, "transformer.ln_f"), self.w["lm_head.weight"])

@@ -164,6 +164,59 @@ def reshape_and_cache(
     _check(rc)
 
 
+def paged_attention_v1_append(
+    out: torch.Tensor,
+    query: torch.Tensor,
+    key: torch.Tensor,
+    value: torch.Tensor,
+    key_cache: torch.Tensor,
+    value_cache: torch.Tensor,
+    slot_mapping: torch.Tensor,
+    num_kv_heads: int,
+    scale: float,
+    block_tables: torch.Tensor,
+    seq_lens: torch.Tensor,
+    block_size: int,
+    max_seq_len: int,
+) -> None:
+    """Extension (no reference counterpart): one launch that does exactly
+    `reshape_and_cache(key, value, key_cache, value_cache, slot_mapping, "auto", 1.0)` followed by
+    `paged_attention_v1(out, query, ...)` for a decode step -- key/value [num_seqs, num_kv_heads, head_size]
+    hold ONE new token per sequence, located at position >= seq_lens[s] - 1 of its sequence."""
+    for t, name in ((out, "out"), (query, "query"), (key, "key"), (value, "value"), (key_cache, "key_cache"),
+                    (value_cache, "value_cache"), (slot_mapping, "slot_mapping"), (block_tables, "block_tables"),
+                    (seq_lens, "seq_lens")):
+        _require_cuda(t, name)
+    if any(t.dtype is not torch.float16 for t in (out, query, key, value, key_cache, value_cache)):
+        raise RuntimeError("vllmini_b200: out, query, key, value and the caches must be float16")
+    if block_tables.dtype is not torch.int32 or seq_lens.dtype is not torch.int32 or slot_mapping.dtype is not torch.int64:
+        raise RuntimeError("vllmini_b200: block_tables/seq_lens must be int32 and slot_mapping int64")
+    num_seqs, num_heads, head_size = query.shape
+    if tuple(key.shape) != (num_seqs, int(num_kv_heads), head_size) or tuple(value.shape) != tuple(key.shape):
+        raise RuntimeError("vllmini_b200: key/value must be [num_seqs, num_kv_heads, head_size] (one token per sequence)")
+    for t in (query, key, value):
+        if t.stride(2) != 1 or t.stride(1) != head_size:
+            raise RuntimeError("vllmini_b200: query/key/value must have contiguous heads")
+    if not (out.is_contiguous() and block_tables.is_contiguous() and seq_lens.is_contiguous()
+            and slot_mapping.is_contiguous() and key_cache.is_contiguous() and value_cache.is_contiguous()):
+        raise RuntimeError("vllmini_b200: out, block_tables, seq_lens, slot_mapping and the caches must be contiguous")
+    dev = query.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    lib = _native.load()
+    ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
+                                                            int(max_seq_len))
+    ws = _workspace(dev, ws_bytes)
+    rc = lib.vb200_paged_attention_v1_append_f16(
+        out.data_ptr(), query.data_ptr(), key.data_ptr(), value.data_ptr(), key_cache.data_ptr(),
+        value_cache.data_ptr(), slot_mapping.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
+        num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size),
+        block_tables.size(1) if block_tables.dim() == 2 else 0, int(max_seq_len),
+        query.stride(0), key.stride(0), value.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
+        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, dev_index,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
+
+
 # ---- binding selection -------------------------------------------------------------------------------
 # The two functions above bind the C ABI through ctypes (no build dependency on torch).  When the compiled
 # torch shim (csrc/torch_shim.cpp -> _torch_shim*.so, `python -m vllmini_b200.build`) is present it replaces
