@@ -3,13 +3,11 @@
 // Behavioural spec: /root/reference/paged_attention_ext/paged_attention_cuda/cache_kernels.cu
 //   :152-207 (kernel), :256-281 (host entry).  Pure copy ("auto" kv-cache dtype) -> bit-exact.
 //
-//   reference: one CTA per token, one thread per scalar: 2-byte loads, 2-byte stores.
-//   here:      one thread per 16-byte chunk (8 dims of one head): one 128-bit load of K and of V,
-//              one 128-bit store into the K cache (its layout keeps 8-dim groups contiguous:
-//              key_cache[blk][h][d/8][off][0..7]) and eight 2-byte stores into the V cache, whose
-//              layout value_cache[blk][h][d][off] makes a token's elements B*2 bytes apart by
-//              construction.  Consecutive lanes take consecutive dim groups, so the K/V reads are
-//              fully coalesced; the grid is flat over (token, chunk).
+//   reference: one CTA per token, one thread per scalar: 2-byte loads, 2-byte stores; consecutive threads
+//              write consecutive head dims, i.e. addresses B*2 bytes apart -> one sector per element.
+//   here:      one CTA per (32-token tile, head): coalesced 128-bit row loads staged in shared memory,
+//              then lane <-> token stores, so that tokens in consecutive slots (prefill) are written as
+//              whole sectors (see reshape_and_cache_tile_kernel).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,37 +17,154 @@
 
 namespace vb200 {
 
-// x == 8, head_size % 8 == 0, 16-byte aligned rows
-__global__ void __launch_bounds__(256) reshape_and_cache_vec8_kernel(
+// x == 8, head_size % 8 == 0, 16-byte aligned rows.
+// One CTA per (32-token tile, head).  Phase 1: the tile's K and V rows (32 x D halves each) are read with
+// coalesced 128-bit loads -- issued before the slots are known, so the slot load and the data loads overlap --
+// and parked in shared memory (row pitch D*2+16 bytes: conflict-free for both access patterns below).
+// Phase 2: lane <-> token.  K: lane stores the 16-byte group g of its token to key_cache[blk][h][g][off][0..7];
+// V: lane stores element d of its token to value_cache[blk][h][d][off].  When consecutive tokens occupy
+// consecutive slots of a block (prefill) the lanes of a store instruction hit consecutive addresses and the
+// LSU coalesces them into whole sectors; with scattered slots (decode) every store is its own sector, which is
+// what the layout dictates.  No run detection, no alignment requirement on the slots.
+constexpr int kTileThreads = 128;
+
+template <int kTileTokens>   // 32, or 16 for small batches (more CTAs in flight)
+__global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
     const __half* __restrict__ key, const __half* __restrict__ value, __half* __restrict__ key_cache,
-    __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int64_t total_chunks,
-    int chunks_per_token, int num_heads, int head_size, int block_size, int64_t key_stride, int64_t value_stride) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_chunks) return;
-  const int64_t t = idx / chunks_per_token;
-  const int c = (int)(idx - t * chunks_per_token);
+    __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads,
+    int head_size, int block_size, int64_t key_stride, int64_t value_stride) {
+  extern __shared__ __align__(16) uint8_t tile_smem[];
+  // head is the fast grid dimension: the CTAs that fill the heads of the same cache blocks run together,
+  // so the partial-sector V writes of a block reach DRAM close in time
+  const int h = blockIdx.x;
+  const int t0 = blockIdx.y * kTileTokens;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int groups = head_size >> 3;        // 16-byte chunks per row
+  const int pitch = head_size * 2 + 16;     // K rows: 16-byte aligned, conflict-free for 128-bit column reads
+  const int vpitch = head_size / 2 + 1;     // V rows in 32-bit words, odd pitch: conflict-free column reads
+  uint8_t* ks = tile_smem;
+  uint32_t* vs = reinterpret_cast<uint32_t*>(tile_smem + kTileTokens * pitch);
+
+  // slot of this lane's token (every warp holds the same 32 slots)
+  const int my_tok = t0 + lane;
+  const int64_t slot = (lane < kTileTokens && my_tok < num_tokens) ? slot_mapping[my_tok] : -1;
+
+  // ---- phase 1: coalesced 128-bit row loads -> smem.  All loads of a batch are issued before the first store
+  //      so a thread pays one memory round trip per batch (the slot load above overlaps too). ----
+  const int nchunks = kTileTokens * groups;
+  constexpr int kBatch = 4;
+  for (int c0 = threadIdx.x; c0 < nchunks; c0 += kTileThreads * kBatch) {
+    uint4 kv[kBatch], vv[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int c = c0 + u * kTileThreads;
+      const int tok = c / groups, g = c - tok * groups;
+      if (c < nchunks && t0 + tok < num_tokens) {
+        kv[u] = ldg128(key + (int64_t)(t0 + tok) * key_stride + (int64_t)h * head_size + g * 8);
+        vv[u] = ldg128(value + (int64_t)(t0 + tok) * value_stride + (int64_t)h * head_size + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int c = c0 + u * kTileThreads;
+      const int tok = c / groups, g = c - tok * groups;
+      if (c < nchunks && t0 + tok < num_tokens) {
+        *reinterpret_cast<uint4*>(ks + tok * pitch + g * 16) = kv[u];
+        uint32_t* vr = vs + tok * vpitch + g * 4;
+        vr[0] = vv[u].x;
+        vr[1] = vv[u].y;
+        vr[2] = vv[u].z;
+        vr[3] = vv[u].w;
+      }
+    }
+  }
+  __syncthreads();
+
+  // Are the tile's tokens (mostly) in consecutive slots?  Every warp holds the same slots -> same answer.
+  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
+  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && slot >= 0 && slot == prev + 1);
+  const bool run_like = __popc(adj) >= kTileTokens / 2;
+
+  if (run_like) {
+    // ---- prefill-like: lane <-> token, so one store instruction covers consecutive slots ----
+    if (slot < 0) return;  // padding token (cache_kernels.cu:166-169); also lanes past num_tokens
+    const int64_t blk = slot / block_size;
+    const int off = (int)(slot % block_size);
+    __half* kdst = key_cache + ((blk * num_heads + h) * (int64_t)groups * block_size + off) * 8;
+    for (int g = warp; g < groups; g += kTileThreads / 32)
+      *reinterpret_cast<uint4*>(kdst + (int64_t)g * block_size * 8) =
+          *reinterpret_cast<const uint4*>(ks + lane * pitch + g * 16);
+    uint16_t* vdst =
+        reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
+    const uint32_t* vrow = vs + lane * vpitch;
+    for (int d2 = warp; d2 < head_size / 2; d2 += kTileThreads / 32) {
+      const uint32_t w = vrow[d2];
+      vdst[(int64_t)(2 * d2) * block_size] = (uint16_t)(w & 0xffffu);
+      vdst[(int64_t)(2 * d2 + 1) * block_size] = (uint16_t)(w >> 16);
+    }
+  } else {
+    // ---- decode-like (scattered slots): warp <-> token, lanes <-> head dims, so the stores of one
+    //      instruction stay inside one (block, head) tile instead of 32 different blocks ----
+    for (int tok = warp; tok < kTileTokens; tok += kTileThreads / 32) {
+      const int64_t s_tok = __shfl_sync(0xffffffffu, slot, tok);
+      if (s_tok < 0) continue;
+      const int64_t blk = s_tok / block_size;
+      const int off = (int)(s_tok % block_size);
+      uint32_t* kdst32 = reinterpret_cast<uint32_t*>(key_cache + (blk * num_heads + h) * (int64_t)head_size * block_size);
+      uint16_t* vdst =
+          reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
+      const uint32_t* krow = reinterpret_cast<const uint32_t*>(ks + tok * pitch);
+      const uint32_t* vrow = vs + tok * vpitch;
+      for (int i = lane; i < head_size / 2; i += 32) {   // 32-bit word i of the row: dims 2i, 2i+1
+        const int g = i >> 2, part = i & 3;
+        kdst32[((int64_t)g * block_size + off) * 4 + part] = krow[i];
+        const uint32_t w = vrow[i];
+        vdst[(int64_t)(2 * i) * block_size] = (uint16_t)(w & 0xffffu);
+        vdst[(int64_t)(2 * i + 1) * block_size] = (uint16_t)(w >> 16);
+      }
+    }
+  }
+}
+
+// Small batches (decode): one warp per (token, head), no shared memory, no CTA barrier.  The slot and the
+// row words are loaded independently (one memory round trip), lanes <-> 32-bit words of the 2*D-byte row.
+__global__ void __launch_bounds__(128) reshape_and_cache_warp_kernel(
+    const __half* __restrict__ key, const __half* __restrict__ value, __half* __restrict__ key_cache,
+    __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads,
+    int head_size, int block_size, int64_t key_stride, int64_t value_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t t = w / num_heads;
+  const int h = (int)(w - t * num_heads);
+  if (t >= num_tokens) return;
   const int64_t slot = slot_mapping[t];
+  const uint32_t* krow = reinterpret_cast<const uint32_t*>(key + t * key_stride + (int64_t)h * head_size);
+  const uint32_t* vrow = reinterpret_cast<const uint32_t*>(value + t * value_stride + (int64_t)h * head_size);
+  constexpr int kMaxWords = 4;  // head_size <= 256
+  uint32_t kw[kMaxWords], vw[kMaxWords];
+#pragma unroll
+  for (int u = 0; u < kMaxWords; ++u) {
+    const int i = lane + 32 * u;
+    if (i < head_size / 2) {
+      kw[u] = __ldg(krow + i);
+      vw[u] = __ldg(vrow + i);
+    }
+  }
   if (slot < 0) return;  // padding token (cache_kernels.cu:166-169)
   const int64_t blk = slot / block_size;
   const int off = (int)(slot % block_size);
-  const int groups = head_size >> 3;
-  const int h = c / groups;
-  const int g = c - h * groups;
-
-  const uint4 kv = ldg128(key + t * key_stride + (int64_t)c * 8);
-  const uint4 vv = ldg128(value + t * value_stride + (int64_t)c * 8);
-
-  // key_cache[blk][h][g][off][0..7]
-  __half* kdst = key_cache + (((blk * num_heads + h) * groups + g) * block_size + off) * 8;
-  *reinterpret_cast<uint4*>(kdst) = kv;
-
-  // value_cache[blk][h][g*8 + i][off]
-  __half* vdst = value_cache + ((blk * num_heads + h) * (int64_t)head_size + g * 8) * block_size + off;
-  const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+  uint32_t* kdst32 = reinterpret_cast<uint32_t*>(key_cache + (blk * num_heads + h) * (int64_t)head_size * block_size);
+  uint16_t* vdst =
+      reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    reinterpret_cast<uint16_t*>(vdst)[(2 * i) * block_size] = (uint16_t)(w[i] & 0xffffu);
-    reinterpret_cast<uint16_t*>(vdst)[(2 * i + 1) * block_size] = (uint16_t)(w[i] >> 16);
+  for (int u = 0; u < kMaxWords; ++u) {
+    const int i = lane + 32 * u;  // 32-bit word i of the row: dims 2i, 2i+1
+    if (i < head_size / 2) {
+      kdst32[((int64_t)(i >> 2) * block_size + off) * 4 + (i & 3)] = kw[u];
+      vdst[(int64_t)(2 * i) * block_size] = (uint16_t)(vw[u] & 0xffffu);
+      vdst[(int64_t)(2 * i + 1) * block_size] = (uint16_t)(vw[u] >> 16);
+    }
   }
 }
 
@@ -96,15 +211,25 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
 
   const bool vec_ok = x == 8 && head_size % 8 == 0 && key_stride % 8 == 0 && value_stride % 8 == 0 &&
                       ((((uintptr_t)key | (uintptr_t)value | (uintptr_t)key_cache) & 15) == 0);
-  if (vec_ok) {
-    const int chunks = num_heads * head_size / 8;
-    const int64_t total = (int64_t)num_tokens * chunks;
-    const int threads = 256;
-    const int64_t blocks = (total + threads - 1) / threads;
-    reshape_and_cache_vec8_kernel<<<(unsigned)blocks, threads, 0, s>>>(
+  if (vec_ok && head_size <= 256 && (num_tokens + 15) / 16 <= 65535) {
+    if (num_tokens <= 512) {  // decode-sized: latency-bound, skip the shared-memory transpose
+      const int64_t warps = (int64_t)num_tokens * num_heads;
+      reshape_and_cache_warp_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(
+          static_cast<const __half*>(key), static_cast<const __half*>(value), static_cast<__half*>(key_cache),
+          static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size, block_size,
+          key_stride, value_stride);
+      count_launch();
+      VB200_CUDA_CHECK(cudaGetLastError());
+      return VB200_OK;
+    }
+    const int tt = num_tokens <= 2048 ? 16 : 32;   // small batches: smaller tiles, more CTAs in flight
+    const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
+    dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
+    auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16> : reshape_and_cache_tile_kernel<32>;
+    kern<<<grid, kTileThreads, smem, s>>>(
         static_cast<const __half*>(key), static_cast<const __half*>(value), static_cast<__half*>(key_cache),
-        static_cast<__half*>(value_cache), slot_mapping, total, chunks, num_heads, head_size, block_size,
-        key_stride, value_stride);
+        static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size, block_size, key_stride,
+        value_stride);
   } else {
     const int n = num_heads * head_size;
     const int64_t total = (int64_t)num_tokens * n;

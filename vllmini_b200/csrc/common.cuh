@@ -120,9 +120,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 }
 
 // ---- vector loads / stores ----
-__device__ __forceinline__ uint4 ldg128(const void* p) {
+__device__ __forceinline__ uint4 ldg128(const void* p) {  // read-only data: not volatile, the compiler may batch
   uint4 r;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
