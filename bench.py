@@ -458,6 +458,34 @@ def run_gpu_arm(args):
     fused_ms = f0.elapsed_time(f1)
     barrier()
 
+    # ---- context row: the timed step replayed from a CUDA graph (the binding is graph-capturable) ----
+    graph_ms = None
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            hp.step(ops)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            hp.step(ops)
+        for _ in range(3):
+            g.replay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            g.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1)
+        del g
+        barrier()
+    except Exception as e:  # context only
+        graph_ms = None
+        print(f"[bench] graph replay skipped: {e!r}", file=sys.stderr)
+
     # ---- timed region 2: host-driven (e2e) ----
     hd = HostDrivenStep(hp)
     for _ in range(warm):
@@ -521,6 +549,11 @@ def run_gpu_arm(args):
                               "ms_per_step": fused_ms / args.steps,
                               "how": "same workload with vb200_paged_attention_v1_append_f16: scatter + attention in "
                                      "one launch per layer (12 launches/step); extension beyond the reference API"}
+        if graph_ms is not None:
+            line["graph_step"] = {"value": world * S / (graph_ms / args.steps * 1e-3), "unit": "tokens/s",
+                                  "ms_per_step": graph_ms / args.steps,
+                                  "how": "the same 24 binding calls captured once in a CUDA graph and replayed "
+                                         "(rank-local, not max-reduced)"}
         if full_model is not None:
             line["full_model"] = full_model
         if world == 1 and not args.no_cpu_baseline:

@@ -149,6 +149,12 @@ uint64_t vb200_launch_count(void);
  * (0 = heuristic) and pipeline variant (0 = default).  Returns the previous packed value. */
 int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant);
 
+/* Programmatic dependent launch (default on): kernels are launched so that their CTAs may become resident
+ * while the previous kernel on the stream drains, and block (griddepcontrol.wait) until it has completed
+ * before reading or writing global memory -- stream-order semantics are unchanged.  Returns the previous
+ * setting.  Turn off if a tool or driver in the stack mishandles programmatic launch attributes. */
+int32_t vb200_set_pdl(int32_t enable);
+
 #ifdef __cplusplus
 }
 #endif

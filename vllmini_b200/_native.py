@@ -33,6 +33,7 @@ SYMBOLS = {
     "vb200_abi_version": (_i32, []),
     "vb200_launch_count": (ctypes.c_uint64, []),
     "vb200_set_tuning": (_i32, [_i32, _i32]),
+    "vb200_set_pdl": (_i32, [_i32]),
 }
 
 _lib = None
@@ -58,6 +59,8 @@ def load() -> ctypes.CDLL:
     got = lib.vb200_abi_version()
     if got != ABI_VERSION:
         raise RuntimeError(f"vllmini_b200: ABI version mismatch: library {got}, binding {ABI_VERSION}; rebuild")
+    if os.environ.get("VLLMINI_B200_NO_PDL"):
+        lib.vb200_set_pdl(0)
     _lib = lib
     return lib
 
@@ -69,6 +72,10 @@ def last_error() -> str:
 
 def launch_count() -> int:
     return int(load().vb200_launch_count())
+
+
+def set_pdl(enable: bool) -> bool:
+    return bool(load().vb200_set_pdl(1 if enable else 0))
 
 
 def set_tuning(force_num_splits: int = 0, variant: int = 0) -> int:

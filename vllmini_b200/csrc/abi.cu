@@ -9,6 +9,9 @@ namespace vb200 {
 
 static thread_local char t_error[512] = {0};
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_pdl{1};
+
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
 char* error_buffer() { return t_error; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -35,4 +38,7 @@ int device_sm_count() {
 
 extern "C" const char* vb200_last_error(void) { return vb200::t_error; }
 extern "C" int32_t vb200_abi_version(void) { return VB200_ABI_VERSION; }
+extern "C" int32_t vb200_set_pdl(int32_t enable) {
+  return vb200::g_pdl.exchange(enable ? 1 : 0, std::memory_order_relaxed);
+}
 extern "C" uint64_t vb200_launch_count(void) { return vb200::g_launches.load(std::memory_order_relaxed); }

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
   const int t0 = blockIdx.y * kTileTokens;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  griddep_launch_dependents();  // PDL: see common.cuh
+  griddep_wait();
   const int groups = head_size >> 3;        // 16-byte chunks per row
   const int pitch = head_size * 2 + 16;     // K rows: 16-byte aligned, conflict-free for 128-bit column reads
   const int vpitch = head_size / 2 + 1;     // V rows in 32-bit words, odd pitch: conflict-free column reads
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(128) reshape_and_cache_warp_kernel(
     __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads,
     int head_size, int block_size, int64_t key_stride, int64_t value_stride) {
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();  // PDL: see common.cuh
+  griddep_wait();
   const int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int64_t t = w / num_heads;
   const int h = (int)(w - t * num_heads);
@@ -214,22 +218,23 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
   if (vec_ok && head_size <= 256 && (num_tokens + 15) / 16 <= 65535) {
     if (num_tokens <= 512) {  // decode-sized: latency-bound, skip the shared-memory transpose
       const int64_t warps = (int64_t)num_tokens * num_heads;
-      reshape_and_cache_warp_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(
-          static_cast<const __half*>(key), static_cast<const __half*>(value), static_cast<__half*>(key_cache),
-          static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size, block_size,
-          key_stride, value_stride);
+      VB200_CUDA_CHECK(launch_kernel(reshape_and_cache_warp_kernel, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, s,
+                                     static_cast<const __half*>(key), static_cast<const __half*>(value),
+                                     static_cast<__half*>(key_cache), static_cast<__half*>(value_cache), slot_mapping,
+                                     num_tokens, num_heads, head_size, block_size, key_stride, value_stride));
       count_launch();
-      VB200_CUDA_CHECK(cudaGetLastError());
       return VB200_OK;
     }
     const int tt = num_tokens <= 2048 ? 16 : 32;   // small batches: smaller tiles, more CTAs in flight
     const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
     dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
     auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16> : reshape_and_cache_tile_kernel<32>;
-    kern<<<grid, kTileThreads, smem, s>>>(
-        static_cast<const __half*>(key), static_cast<const __half*>(value), static_cast<__half*>(key_cache),
-        static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size, block_size, key_stride,
-        value_stride);
+    VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(kTileThreads), (size_t)smem, s, static_cast<const __half*>(key),
+                                   static_cast<const __half*>(value), static_cast<__half*>(key_cache),
+                                   static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size,
+                                   block_size, key_stride, value_stride));
+    count_launch();
+    return VB200_OK;
   } else {
     const int n = num_heads * head_size;
     const int64_t total = (int64_t)num_tokens * n;

@@ -49,10 +49,37 @@ struct DeviceGuard {
   }
 };
 
+// Programmatic dependent launch (PDL): when enabled, kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that their CTAs can become resident while the previous
+// kernel on the stream drains; every kernel calls griddep_wait() before it touches global memory, which blocks
+// until the previous kernel has completed and flushed (so stream-order semantics are unchanged).
+bool pdl_enabled();                // abi.cu (vb200_set_pdl)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // device: PTX wrappers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// PDL: let the next kernel on the stream start scheduling its CTAs / block until the previous kernel is done.
+// Both are no-ops when the kernel was launched without the programmatic attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -345,6 +345,17 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
+  // PDL: this CTA may have become resident while the previous kernel on the stream was still draining.  Let
+  // our own successor do the same, set up the barriers, then wait for the predecessor before the first global
+  // access (seq_lens, block tables, q and the caches may all be its outputs).
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + PaCfg<D, B, W, NST>::BAR_OFF) + i * 8, 1);
+    fence_mbar_init();
+  }
+  griddep_wait();
+
   const UnitRange r = unit_range<B>(p, seq, split);
   if (r.empty_split) return;
   const int nstages = r.nstages, nblk = r.nblk;
@@ -358,11 +369,6 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const uint32_t pbuf = smem_u32(smem + C::PBUF_OFF) + warp * 64;
   const uint32_t bars = smem_u32(smem + C::BAR_OFF) + warp * (NST * 8);
 
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + C::BAR_OFF) + i * 8, 1);
-    fence_mbar_init();
-  }
   // ---- fused append: the CTA of the LAST live split of (seq, head) first writes this step's K/V row of its
   //      kv head into the caches -- the same element moves as reshape_and_cache (cache_kernels.cu:178-199) --
   //      then fences generic -> async proxy so that its own bulk copies read the new row.  Contract: the new
@@ -485,6 +491,8 @@ __global__ void __launch_bounds__((W + 1) * 32) pa_v1_persistent_kernel(const Pa
     }
     fence_mbar_init();
   }
+  griddep_launch_dependents();
+  griddep_wait();
   __syncthreads();
 
   // =================================== scheduler warp ===================================
@@ -673,9 +681,8 @@ static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) 
     attr_set[dev] = true;
   }
   dim3 grid(p.num_heads, num_seqs, p.num_splits);
-  kern<<<grid, W * 32, C::SMEM, stream>>>(p);
+  VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
   count_launch();
-  VB200_CUDA_CHECK(cudaGetLastError());
   return VB200_OK;
 }
 
@@ -698,9 +705,8 @@ static int launch_persistent(const PaParams& p, int num_seqs, int* sched, cudaSt
   const long long num_units = (long long)num_seqs * p.num_heads * p.num_splits;
   if (num_units > 0x7fffffffLL - 65536) return set_error(VB200_ERR_INVALID_ARGUMENT, "too many work units");
   const int grid = num_units < resident[dev] ? (int)num_units : resident[dev];
-  kern<<<grid, kThreads, C::SMEM, stream>>>(p, (int)num_units, sched);
+  VB200_CUDA_CHECK(launch_kernel(kern, dim3(grid), dim3(kThreads), (size_t)C::SMEM, stream, p, (int)num_units, sched));
   count_launch();
-  VB200_CUDA_CHECK(cudaGetLastError());
   return VB200_OK;
 }
 
