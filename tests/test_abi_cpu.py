@@ -51,7 +51,7 @@ def test_library_has_sm100a_code_and_blackwell_instructions():
         pytest.skip("cuobjdump not available")
     elf = subprocess.run([cuobjdump, "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5vb20012pa_v1_kernelILi64ELi16ELi4ELi2EEEvNS_8PaParamsE",
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5vb20012pa_v1_kernelILi64ELi16ELi4ELi2ELb0EEEvNS_8PaParamsE",
                            _native.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UBLKCP", "SYNCS.ARRIVE.TRANS64", "FHFMA", "CREDUX.MAX.F32", "LDS.128"):
         assert mnemonic in sass, mnemonic

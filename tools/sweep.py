@@ -47,6 +47,9 @@ def algorithmic_bytes(S, H, D, B, lens):
     return kv + 2 * S * H * D * 2 + sum(((int(l) + B - 1) // B) * 4 for l in lens) + S * 4
 
 
+POOL_MULT = 1   # --pool-mult: KV pool this many times larger than the batch needs (block ids spread over it)
+
+
 def make(S, H, D, B, ctx, seed, dev, mixed=False):
     g = torch.Generator(device=dev).manual_seed(seed)
     if mixed:
@@ -54,11 +57,11 @@ def make(S, H, D, B, ctx, seed, dev, mixed=False):
     else:
         lens = torch.full((S,), ctx, dtype=torch.int32, device=dev)
     nblk = (int(lens.max()) + B - 1) // B
-    NB = S * nblk
-    kc = torch.randn(NB, H, D // 8, B, 8, generator=g, device=dev, dtype=torch.float16)
-    vc = torch.randn(NB, H, D, B, generator=g, device=dev, dtype=torch.float16)
+    NB = S * nblk * POOL_MULT
+    kc = torch.empty(NB, H, D // 8, B, 8, device=dev, dtype=torch.float16).normal_(generator=g)
+    vc = torch.empty(NB, H, D, B, device=dev, dtype=torch.float16).normal_(generator=g)
     q = torch.randn(S, H, D, generator=g, device=dev, dtype=torch.float16)
-    bt = torch.randperm(NB, generator=g, device=dev).to(torch.int32).view(S, nblk)
+    bt = torch.randperm(NB, generator=g, device=dev)[: S * nblk].to(torch.int32).view(S, nblk).contiguous()
     return q, kc, vc, bt, lens
 
 
@@ -122,9 +125,12 @@ def main():
     ap.add_argument("--variants", default="0,1,2")
     ap.add_argument("--splits", default="0")
     ap.add_argument("--ref", action="store_true", help="also time the reference's own kernel (oracle/_ref)")
+    ap.add_argument("--pool-mult", type=int, default=1)
     ap.add_argument("--graph", action="store_true", help="time launches replayed from a CUDA graph (no host overhead)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     a = ap.parse_args()
+    global POOL_MULT
+    POOL_MULT = a.pool_mult
     res = []
     ref = None
     if a.ref:

@@ -333,7 +333,7 @@ __device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int 
 // ---------------------------------------------------------------------------------------------
 // Classic kernel: one CTA per (head, seq, split)
 // ---------------------------------------------------------------------------------------------
-template <int D, int B, int W, int NST>
+template <int D, int B, int W, int NST, bool APPEND>
 __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   using C = PaCfg<D, B, W, NST>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -369,25 +369,31 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const uint32_t pbuf = smem_u32(smem + C::PBUF_OFF) + warp * 64;
   const uint32_t bars = smem_u32(smem + C::BAR_OFF) + warp * (NST * 8);
 
-  // ---- fused append: the CTA of the LAST live split of (seq, head) first writes this step's K/V row of its
-  //      kv head into the caches -- the same element moves as reshape_and_cache (cache_kernels.cu:178-199) --
-  //      then fences generic -> async proxy so that its own bulk copies read the new row.  Contract: the new
-  //      token sits at position >= seq_len - 1 (seq_len - 1 when it attends to itself, seq_len with the
-  //      reference scheduler's convention), so no other split reads that slot. ----
-  if (p.new_k != nullptr && split == r.nsplit_seq - 1) {
-    const int64_t slot = p.slot_mapping[seq];
-    if (slot >= 0) {
-      const int64_t blk = slot / B;
-      const int off = (int)(slot % B);
-      __half* kdst = p.kc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
-      __half* vdst = p.vc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
-      const __half* ksrc = p.new_k + (int64_t)seq * p.new_k_stride + (int64_t)kv_head * D;
-      const __half* vsrc = p.new_v + (int64_t)seq * p.new_v_stride + (int64_t)kv_head * D;
-      for (int i = threadIdx.x; i < D / 8; i += W * 32)
-        *reinterpret_cast<uint4*>(kdst + ((int64_t)i * B + off) * 8) = ldg128(ksrc + i * 8);
-      for (int i = threadIdx.x; i < D; i += W * 32) vdst[(int64_t)i * B + off] = vsrc[i];
-      fence_proxy_async_global();
-    }
+  // ---- fused append (APPEND instantiation only): the CTA of the LAST live split of (seq, head) also stores this
+  //      step's K/V row of its kv head into the caches -- the same element moves as reshape_and_cache
+  //      (cache_kernels.cu:178-199).  Nothing of it sits on the critical path: the warp that owns the last
+  //      stage prefetches the slot and the row into registers now, patches the row into its shared-memory
+  //      tile when that stage has landed (if the row is the newest attended token, position seq_len - 1; the
+  //      bulk copy may have raced with nothing, the row is not in global memory yet), and writes the row to
+  //      global memory after its last stage.  Contract: the new token is at position >= seq_len - 1, so no
+  //      other split reads that slot. ----
+  const int row_warp = nstages > 0 ? (nstages - 1) % W : 0;
+  const bool row_owner = APPEND && p.new_k != nullptr && split == r.nsplit_seq - 1 && warp == row_warp;
+  int64_t new_slot = -1;
+  int64_t phys_last = -1;
+  uint4 patch_k = make_uint4(0, 0, 0, 0);   // lane g < D/8: the row's 16-byte group g
+  uint32_t patch_v[(D + 63) / 64];          // lane: words lane, lane + 32, ... of the V row (2 dims per word)
+#pragma unroll
+  for (int u = 0; u < (D + 63) / 64; ++u) patch_v[u] = 0;
+  if (row_owner) {
+    new_slot = p.slot_mapping[seq];
+    const __half* ksrc = p.new_k + (int64_t)seq * p.new_k_stride + (int64_t)kv_head * D;
+    const __half* vsrc = p.new_v + (int64_t)seq * p.new_v_stride + (int64_t)kv_head * D;
+    if (lane < D / 8) patch_k = ldg128(ksrc + lane * 8);
+#pragma unroll
+    for (int u = 0; u < (D + 63) / 64; ++u)
+      if (lane + 32 * u < D / 2) patch_v[u] = __ldg(reinterpret_cast<const uint32_t*>(vsrc) + lane + 32 * u);
+    if (nstages > 0) phys_last = __ldg(table + (r.tok_end - 1 - r.tok_begin) / B);
   }
   __syncthreads();
 
@@ -430,6 +436,25 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   for (int st = warp; st < nstages; st += W, ++k) {
     const int slot = k % NST;
     mbar_wait(bars + slot * 8, (k / NST) & 1);
+    if (APPEND && row_owner && st == nstages - 1 && new_slot >= 0 &&
+        new_slot == phys_last * B + (r.tok_end - 1) % B) {
+      // the new row is the newest attended token: put it into the landed tiles of this (last) stage
+      const int in_stage = (r.tok_end - 1 - r.tok_begin) - st * 32;   // 0..31
+      const int b = in_stage / B;
+      const int off = (int)(new_slot % B);
+      uint8_t* kt = smem + (warp * NST + slot) * C::STAGE + b * C::TILE;
+      uint8_t* vt = smem + (warp * NST + slot) * C::STAGE + (C::BPS + b) * C::TILE;
+      if (lane < D / 8) *reinterpret_cast<uint4*>(kt + (lane * B + off) * 16) = patch_k;
+#pragma unroll
+      for (int u = 0; u < (D + 63) / 64; ++u) {
+        const int i = lane + 32 * u;   // dims 2i, 2i+1
+        if (i < D / 2) {
+          reinterpret_cast<uint16_t*>(vt)[(2 * i) * B + off] = (uint16_t)(patch_v[u] & 0xffffu);
+          reinterpret_cast<uint16_t*>(vt)[(2 * i + 1) * B + off] = (uint16_t)(patch_v[u] >> 16);
+        }
+      }
+      __syncwarp();
+    }
     process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, m, lsum, acc, r.tok_begin + st * 32, r.tok_end,
                      p.scale_log2e);
     // ---- refill this slot with the stage NST rounds ahead ----
@@ -437,6 +462,23 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
     if (st_next < nstages) {
       issue_stage(st_next, slot, next_phys);
       next_phys = (st_next + W < nstages) ? load_phys(st_next + W) : 0;
+    }
+  }
+
+  if (APPEND && row_owner && new_slot >= 0) {  // fused append: the row goes to the caches, off the critical path
+    const int64_t blk = new_slot / B;
+    const int off = (int)(new_slot % B);
+    __half* kdst = p.kc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
+    uint16_t* vdst =
+        reinterpret_cast<uint16_t*>(p.vc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride) + off;
+    if (lane < D / 8) *reinterpret_cast<uint4*>(kdst + ((int64_t)lane * B + off) * 8) = patch_k;
+#pragma unroll
+    for (int u = 0; u < (D + 63) / 64; ++u) {
+      const int i = lane + 32 * u;
+      if (i < D / 2) {
+        vdst[(int64_t)(2 * i) * B] = (uint16_t)(patch_v[u] & 0xffffu);
+        vdst[(int64_t)(2 * i + 1) * B] = (uint16_t)(patch_v[u] >> 16);
+      }
     }
   }
 
@@ -669,10 +711,10 @@ static constexpr Variant kVariants[] = {{4, 2, false}, {4, 3, false}, {8, 1, fal
                                         {4, 2, true},  {8, 1, true},  {4, 3, true},  {2, 2, true}};
 constexpr int kNumVariants = 8;
 
-template <int D, int B, int W, int NST>
-static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
+template <int D, int B, int W, int NST, bool APPEND>
+static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
   using C = PaCfg<D, B, W, NST>;
-  auto kern = pa_v1_kernel<D, B, W, NST>;
+  auto kern = pa_v1_kernel<D, B, W, NST, APPEND>;
   static bool attr_set[64] = {};
   int dev = 0;
   VB200_CUDA_CHECK(cudaGetDevice(&dev));
@@ -684,6 +726,14 @@ static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) 
   VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
   count_launch();
   return VB200_OK;
+}
+
+template <int D, int B, int W, int NST>
+static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
+  if (p.new_k != nullptr) {
+    if constexpr (W == 4 && NST == 2) return launch_classic_impl<D, B, 4, 2, true>(p, num_seqs, stream);
+  }
+  return launch_classic_impl<D, B, W, NST, false>(p, num_seqs, stream);
 }
 
 template <int D, int B, int W, int NST>
@@ -864,7 +914,7 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.new_v_stride = a.new_v_stride;
   p.kc_w = static_cast<__half*>(const_cast<void*>(key_cache));
   p.vc_w = static_cast<__half*>(const_cast<void*>(value_cache));
-  if (a.new_k != nullptr && kVariants[variant].persistent) variant = 0;  // the fused append lives in the classic kernel
+  if (a.new_k != nullptr) variant = 0;  // the fused append lives in the default classic instantiation
   if (ns > 1) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
     p.ws_cnt = static_cast<int32_t*>(workspace) + kSchedWords;
