@@ -446,21 +446,25 @@ def run_gpu_arm(args):
             q, k, v = hp.views(hp.qkv, l)
             ops.paged_attention_v1_append(hp.out[l], q, k, v, hp.key_cache, hp.value_cache, hp.slots[l], H, hp.scale,
                                           hp.block_tables[l], hp.seq_lens, B, CTX)
-    for _ in range(3):
-        fused_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        fused_step()
-    f1.record()
-    torch.cuda.synchronize()
-    fused_ms = f0.elapsed_time(f1)
-    barrier()
+    fused_ms = 0.0
+    if not args.no_extras:
+        for _ in range(3):
+            fused_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fused_step()
+        f1.record()
+        torch.cuda.synchronize()
+        fused_ms = f0.elapsed_time(f1)
+        barrier()
 
     # ---- context row: the timed step replayed from a CUDA graph (the binding is graph-capturable) ----
     graph_ms = None
     try:
+        if args.no_extras:
+            raise RuntimeError("skipped (--no-extras)")
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -484,7 +488,8 @@ def run_gpu_arm(args):
         barrier()
     except Exception as e:  # context only
         graph_ms = None
-        print(f"[bench] graph replay skipped: {e!r}", file=sys.stderr)
+        if not args.no_extras:
+            print(f"[bench] graph replay skipped: {e!r}", file=sys.stderr)
 
     # ---- timed region 2: host-driven (e2e) ----
     hd = HostDrivenStep(hp)
@@ -545,10 +550,11 @@ def run_gpu_arm(args):
                          "launches_timed": len(attn_us), "attention_share_of_step": attn_mean_us * LAYERS / (ms_step * 1e3),
                          "traffic": recorded_traffic()},
         }
-        line["fused_step"] = {"value": world * S / (fused_ms / args.steps * 1e-3), "unit": "tokens/s",
-                              "ms_per_step": fused_ms / args.steps,
-                              "how": "same workload with vb200_paged_attention_v1_append_f16: scatter + attention in "
-                                     "one launch per layer (12 launches/step); extension beyond the reference API"}
+        if fused_ms > 0:
+            line["fused_step"] = {"value": world * S / (fused_ms / args.steps * 1e-3), "unit": "tokens/s",
+                                  "ms_per_step": fused_ms / args.steps,
+                                  "how": "same workload with vb200_paged_attention_v1_append_f16: scatter + attention "
+                                         "in one launch per layer (12 launches/step); extension beyond the reference API"}
         if graph_ms is not None:
             line["graph_step"] = {"value": world * S / (graph_ms / args.steps * 1e-3), "unit": "tokens/s",
                                   "ms_per_step": graph_ms / args.steps,
@@ -576,6 +582,7 @@ def main():
     ap.add_argument("--impl", default="vllmini_b200", choices=["vllmini_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-model", action="store_true", help="skip the whole-GPT-2 decode context row")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fused_step / graph_step context rows")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
