@@ -511,3 +511,98 @@ def test_fused_append_equals_reshape_then_attention(self_attend, shape):
     truth = po.paged_attention_v1_exact(q, kc_a.cpu().numpy(), vc_a.cpu().numpy(), 0.1, bt, seq_lens.cpu().numpy(),
                                         num_kv_heads=KVH)
     assert_close_to_truth(out_b.cpu().numpy(), truth, what="fused append")
+
+
+# ------------------------------------------------------------------------------ randomized shapes
+def test_randomized_shapes_against_c_oracle():
+    """60 seeded random problems: batch 1..40, heads (MHA and GQA), head size 64/128, block 8/16/32, ragged
+    lengths 0..700, padded tables, strided queries, random max_seq_len slack -- all against the fp64 oracle."""
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(2024)
+    co = c_oracle()
+    dev = torch.device("cuda:0")
+    worst = 0.0
+    for trial in range(60):
+        D = int(rng.choice([64, 128]))
+        B = int(rng.choice([8, 16, 32]))
+        KVH = int(rng.choice([1, 2, 4, 12]))
+        H = KVH * int(rng.choice([1, 1, 2, 4]))
+        S = int(rng.integers(1, 41))
+        hi = int(rng.choice([20, 100, 700]))
+        lens = rng.integers(0, hi + 1, size=S).astype(np.int32)
+        if trial % 7 == 0:
+            lens[:] = int(rng.integers(1, hi + 1))
+        mb = int(max((int(lens.max()) + B - 1) // B, 1)) + int(rng.integers(0, 3))
+        q, kc, vc, bt, sl = po.make_case(S, KVH, D, B, lens, seed=trial, max_blocks_per_seq=mb,
+                                         num_blocks=int(((lens.astype(np.int64) + B - 1) // B).sum()) + 3)
+        pad = int(rng.choice([0, 8, 2 * H * D]))
+        qbuf = rng.standard_normal((S, H * D + pad)).astype(np.float16)
+        q_np = qbuf[:, :H * D].reshape(S, H, D)
+        q_t = torch.from_numpy(qbuf).to(dev)[:, :H * D].view(S, H, D)
+        assert q_t.stride(0) == H * D + pad
+        out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+        scale = float(rng.choice([D ** -0.5, 0.05, 0.3]))
+        msl = mb * B if trial % 3 else max(int(lens.max()), 1)
+        ops.paged_attention_v1(out, q_t, torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev), KVH, scale,
+                               torch.from_numpy(bt).to(dev), torch.from_numpy(sl).to(dev), B, msl, None, "auto", 1.0,
+                               0, 0, 1, 1, 0)
+        torch.cuda.synchronize()
+        truth = co.paged_attention_v1(np.ascontiguousarray(q_np), kc, vc, scale, bt, sl, num_kv_heads=KVH,
+                                      mode="exact").astype(np.float64)
+        worst = max(worst, assert_close_to_truth(out.cpu().numpy(), truth, atol=1.5e-3,
+                                                 what=f"trial {trial} S={S} H={H}/{KVH} D={D} B={B}"))
+    assert worst < 2.5e-3
+
+
+# ------------------------------------------------------------------------------ BASELINE configs at full size
+def _device_case(S, H, D, B, lens, seed):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lens_t = torch.as_tensor(lens, dtype=torch.int32, device=dev)
+    nblk = (int(lens_t.max()) + B - 1) // B
+    NB = S * nblk
+    kc = torch.empty(NB, H, D // 8, B, 8, device=dev, dtype=torch.float16).normal_(generator=g)
+    vc = torch.empty(NB, H, D, B, device=dev, dtype=torch.float16).normal_(generator=g)
+    q = torch.randn(S, H, D, generator=g, device=dev, dtype=torch.float16)
+    bt = torch.randperm(NB, generator=g, device=dev).to(torch.int32).view(S, nblk)
+    return q, kc, vc, bt, lens_t
+
+
+@pytest.mark.parametrize("name,S,H,D,B,ctx", [
+    ("configs[1] bs=64 ctx=512", 64, 12, 64, 16, 512),
+    ("metric bs=256 ctx=1024", 256, 12, 64, 16, 1024),
+    ("configs[2] mixed 128-2048", 256, 12, 64, 16, -2048),
+    ("configs[3] blk8 ctx4k 20x64", 256, 20, 64, 8, 4096),
+    ("configs[3] blk32 ctx8k 20x64", 256, 20, 64, 32, 8192),
+])
+def test_baseline_configs_full_size_vs_reference_kernel(name, S, H, D, B, ctx, ref_ext):
+    """Every BASELINE.json config at its real size: the new kernel against the reference's own kernel on the
+    same tensors (tolerance of SURVEY.md 8c), plus an fp64-oracle spot check on two sequences."""
+    if ref_ext is None:
+        pytest.skip("oracle/_ref not built")
+    from vllmini_b200 import ops
+    if ctx < 0:
+        lens = torch.randint(128, -ctx + 1, (S,), generator=torch.Generator().manual_seed(0)).tolist()
+    else:
+        lens = [ctx] * S
+    q, kc, vc, bt, sl = _device_case(S, H, D, B, lens, seed=S + B)
+    msl = int(bt.shape[1]) * B
+    new = torch.empty_like(q)
+    ref = torch.empty_like(q)
+    ops.paged_attention_v1(new, q, kc, vc, H, D ** -0.5, bt, sl, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    ref_ext.paged_attention_v1(ref, q, kc, vc, H, D ** -0.5, bt, sl, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    torch.cuda.synchronize()
+    diff = (new.float() - ref.float()).abs()
+    assert bool((diff <= ATOL_VS_REF + RTOL_VS_REF * ref.float().abs()).all()), f"{name}: max diff {diff.max().item():.3e}"
+    rows = [0, S - 1]
+    kc_np, vc_np = None, None
+    # gather only the blocks of the two spot-check sequences for the CPU oracle
+    used = torch.unique(bt[rows].flatten()).long()
+    remap = torch.full((kc.shape[0],), -1, dtype=torch.int32, device=kc.device)
+    remap[used] = torch.arange(used.numel(), dtype=torch.int32, device=kc.device)
+    truth = c_oracle().paged_attention_v1(q[rows].cpu().numpy(), kc[used].cpu().numpy(), vc[used].cpu().numpy(),
+                                          D ** -0.5, remap[bt[rows].long()].cpu().numpy(), sl[rows].cpu().numpy(),
+                                          mode="exact").astype(np.float64)
+    err_new = np.abs(new[rows].cpu().numpy().astype(np.float64) - truth).max()
+    err_ref = np.abs(ref[rows].cpu().numpy().astype(np.float64) - truth).max()
+    assert err_new <= max(5e-4, err_ref), f"{name}: new {err_new:.2e} vs reference kernel {err_ref:.2e} from fp64 truth"
