@@ -539,7 +539,7 @@ def test_randomized_shapes_against_c_oracle():
         qbuf = rng.standard_normal((S, H * D + pad)).astype(np.float16)
         q_np = qbuf[:, :H * D].reshape(S, H, D)
         q_t = torch.from_numpy(qbuf).to(dev)[:, :H * D].view(S, H, D)
-        assert q_t.stride(0) == H * D + pad
+        assert S == 1 or q_t.stride(0) == H * D + pad      # torch normalises strides of size-1 dims
         out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
         scale = float(rng.choice([D ** -0.5, 0.05, 0.3]))
         msl = mb * B if trial % 3 else max(int(lens.max()), 1)
