@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""CTA timeline of one paged_attention_v1 launch (needs lib/libvllmini_b200_trace.so built with -DVB200_TRACE).
+
+Prints where the launch's wall time goes: ramp-up, steady state, tail; per-CTA prologue and lifetime."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from sweep import CONFIGS, make  # noqa: E402
+
+lib = ctypes.CDLL(os.path.join(ROOT, "vllmini_b200", "lib", "libvllmini_b200_trace.so"))
+vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+lib.vb200_paged_attention_v1_f16.argtypes = [vp] * 6 + [i32] * 7 + [i64] * 3 + [f32, vp, sz, i32, vp]
+lib.vb200_debug_set_trace.argtypes = [vp]
+lib.vb200_set_pdl.argtypes = [i32]
+
+
+def run(name):
+    S, H, D, B, ctx = CONFIGS[name]
+    mixed = ctx < 0
+    ctx = abs(ctx)
+    dev = torch.device("cuda:0")
+    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(2)]
+    nctas = S * H
+    trace = torch.zeros(nctas * 4, dtype=torch.int64, device=dev)
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def call(i, tr):
+        q, kc, vc, bt, sl = pools[i % 2]
+        out = torch.empty_like(q)
+        lib.vb200_debug_set_trace(tr)
+        rc = lib.vb200_paged_attention_v1_f16(out.data_ptr(), q.data_ptr(), kc.data_ptr(), vc.data_ptr(), bt.data_ptr(),
+                                              sl.data_ptr(), S, H, H, D, B, bt.shape[1], ctx, q.stride(0), kc.stride(0),
+                                              kc.stride(1), D ** -0.5, ws.data_ptr(), ws.numel(), 0, stream)
+        assert rc == 0
+    for i in range(4):
+        call(i, None)
+    torch.cuda.synchronize()
+    call(0, trace.data_ptr())
+    torch.cuda.synchronize()
+    t = trace.cpu().numpy().reshape(nctas, 4).astype(np.int64)
+    smid, t0, t1, t2 = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+    base = t0.min()
+    t0, t1, t2 = (t0 - base) / 1e3, (t1 - base) / 1e3, (t2 - base) / 1e3     # us
+    span = t2.max()
+    life = t2 - t0
+    prol = t1 - t0
+    # concurrency over time
+    ev = np.concatenate([np.stack([t0, np.ones_like(t0)], 1), np.stack([t2, -np.ones_like(t2)], 1)])
+    ev = ev[np.argsort(ev[:, 0])]
+    conc = np.cumsum(ev[:, 1])
+    full = conc.max()
+    # time until concurrency first reaches 95 % of max; time after it last drops below 95 %
+    hi = np.nonzero(conc >= 0.95 * full)[0]
+    ramp_end, tail_start = ev[hi[0], 0], ev[hi[-1] + 1, 0] if hi[-1] + 1 < len(ev) else span
+    rep = {
+        "config": name, "ctas": int(nctas), "span_us": float(span), "max_concurrent_ctas": int(full),
+        "ramp_until_95pct_resident_us": float(ramp_end), "tail_below_95pct_us": float(span - tail_start),
+        "first_data_after_start_us": {"p10": float(np.percentile(prol, 10)), "p50": float(np.percentile(prol, 50)),
+                                       "p90": float(np.percentile(prol, 90))},
+        "cta_lifetime_us": {"p10": float(np.percentile(life, 10)), "p50": float(np.percentile(life, 50)),
+                            "p90": float(np.percentile(life, 90)), "max": float(life.max())},
+        "first_wave_first_data_us": float(np.percentile(t1[t0 < 1.0], 50)),
+        "last_cta_start_us": float(t0.max()), "sms_used": int(len(np.unique(smid))),
+        "cta_seconds_total_us": float(life.sum()), "avg_concurrency": float(life.sum() / span),
+    }
+    # idle SM-slot time in the tail: for each SM, time between its last CTA end and the span end
+    last_end = np.array([t2[smid == s].max() for s in np.unique(smid)])
+    rep["sm_idle_at_end_us"] = {"mean": float((span - last_end).mean()), "max": float((span - last_end).max())}
+    return rep
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["M"]
+    for pdl in (0,):
+        lib.vb200_set_pdl(pdl)
+        for n in names:
+            print(json.dumps(run(n)))

@@ -60,6 +60,9 @@ struct PaParams {
   int64_t new_v_stride;
   __half* kc_w;
   __half* vc_w;
+#ifdef VB200_TRACE
+  unsigned long long* trace;  // [num_ctas][4]: smid, t_start, t_first_data, t_end (globaltimer ns)
+#endif
 };
 
 template <int D, int B, int W, int NST>
@@ -348,6 +351,10 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   // PDL: this CTA may have become resident while the previous kernel on the stream was still draining.  Let
   // our own successor do the same, set up the barriers, then wait for the predecessor before the first global
   // access (seq_lens, block tables, q and the caches may all be its outputs).
+#ifdef VB200_TRACE
+  unsigned long long t_start = 0, t_first = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -436,6 +443,9 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   for (int st = warp; st < nstages; st += W, ++k) {
     const int slot = k % NST;
     mbar_wait(bars + slot * 8, (k / NST) & 1);
+#ifdef VB200_TRACE
+    if (threadIdx.x == 0 && k == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+#endif
     if (APPEND && row_owner && st == nstages - 1 && new_slot >= 0 &&
         new_slot == phys_last * B + (r.tok_end - 1) % B) {
       // the new row is the newest attended token: put it into the landed tiles of this (last) stage
@@ -486,6 +496,19 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   warp_publish<C>(red, warp, lane, m, lsum, acc);
   __syncthreads();
   cta_merge_and_store<C, W, 1>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, &s_last);
+#ifdef VB200_TRACE
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    unsigned long long t_end;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    p.trace[cta * 4 + 0] = smid;
+    p.trace[cta * 4 + 1] = t_start;
+    p.trace[cta * 4 + 2] = t_first;
+    p.trace[cta * 4 + 3] = t_end;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -692,6 +715,11 @@ __global__ void __launch_bounds__((W + 1) * 32) pa_v1_persistent_kernel(const Pa
 // --------------------------------------------------------------------------------------------
 constexpr int kCounterCap = 16384;  // int32 words at the start of the workspace: [0..15] scheduler, rest split counters
 constexpr int kSchedWords = 16;
+
+#ifdef VB200_TRACE
+static unsigned long long* g_trace = nullptr;
+extern "C" void vb200_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
+#endif
 
 struct Tuning {
   int force_splits = 0;
@@ -914,6 +942,9 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.new_v_stride = a.new_v_stride;
   p.kc_w = static_cast<__half*>(const_cast<void*>(key_cache));
   p.vc_w = static_cast<__half*>(const_cast<void*>(value_cache));
+#ifdef VB200_TRACE
+  p.trace = g_trace;
+#endif
   if (a.new_k != nullptr) variant = 0;  // the fused append lives in the default classic instantiation
   if (ns > 1) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
