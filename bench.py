@@ -42,7 +42,16 @@ if ROOT not in sys.path:
 S, H, D, B, CTX, LAYERS = 256, 12, 64, 16, 1024, 12
 WORKLOAD = ("gpt2-small decode hot path: 12 layers x (reshape_and_cache + paged_attention_v1), "
             "bs=256/GPU, ctx=1024, heads 12x64, block_size=16, fp16")
-METRIC = "decode tokens/sec @ bs=256 ctx=1024 GPT-2 (paged-attention hot path)"
+def _baseline_metric():
+    """`metric` is BASELINE.json's, verbatim."""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "decode tokens/sec @ bs=256 ctx=1024 GPT-2; paged-attn HBM GB/s vs 8 TB/s peak"
+
+
+METRIC = _baseline_metric()
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -289,10 +298,30 @@ class HostDrivenStep:
         self.h2d = self.h_in.numel() + self.h_sl.numel() * 4
         self.d2h = self.h_out.numel() * 2
 
+    def capture(self, ops):
+        """Capture one host-driven step (copies on the side streams + the binding calls) in a CUDA graph; the
+        pinned host buffers keep their addresses, so a step becomes: fill h_in -> replay -> sync -> read h_out."""
+        torch = self.torch
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue(ops, torch.cuda.current_stream(self.hp.dev), final_join=True)
+
+    def step_graph(self):
+        self.graph.replay()
+        self.torch.cuda.current_stream(self.hp.dev).synchronize()
+        return self.h_out
+
     def step(self, ops):
         torch, hp = self.torch, self.hp
         cur = torch.cuda.current_stream(hp.dev)
+        self._enqueue(ops, cur, final_join=False)
+        self.s_out.synchronize()
+        return self.h_out
+
+    def _enqueue(self, ops, cur, final_join):
+        torch, hp = self.torch, self.hp
         self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
         with torch.cuda.stream(self.s_in):
             self.d_sl.copy_(self.h_sl, non_blocking=True)
         for l in range(LAYERS):
@@ -311,8 +340,9 @@ class HostDrivenStep:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_out[l])
                 self.h_out[l].copy_(self.d_out[l], non_blocking=True)
-        self.s_out.synchronize()
-        return self.h_out
+        if final_join:
+            cur.wait_stream(self.s_in)
+            cur.wait_stream(self.s_out)
 
 
 def run_full_model(args, dev, world, rank):
@@ -495,10 +525,21 @@ def run_gpu_arm(args):
     hd = HostDrivenStep(hp)
     for _ in range(warm):
         hd.step(ops)
+    e2e_mode = "eager enqueue"
+    e2e_step = lambda: hd.step(ops)                      # noqa: E731
+    if not args.e2e_eager:
+        try:                                             # the binding is graph-capturable: one replay per step
+            torch.cuda.synchronize()
+            hd.capture(ops)
+            for _ in range(warm):
+                hd.step_graph()
+            e2e_step, e2e_mode = hd.step_graph, "CUDA-graph replay"
+        except Exception as e:
+            print(f"[bench] e2e graph capture failed, using eager enqueue: {e!r}", file=sys.stderr)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        hd.step(ops)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -539,7 +580,7 @@ def run_gpu_arm(args):
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "how": "per layer one packed pinned buffer (q/k/v + slot mapping + block table) -> device, "
                            "2 launches through the binding, attention output -> pinned host; copies pipelined "
-                           "against compute on 3 streams; host sync every step"},
+                           "against compute on 3 streams; host sync every step; step issued by " + e2e_mode},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "vb200::pa_v1_kernel<64,16,4,2>", "achieved": achieved, "peak": peak,
@@ -582,6 +623,7 @@ def main():
     ap.add_argument("--impl", default="vllmini_b200", choices=["vllmini_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-model", action="store_true", help="skip the whole-GPT-2 decode context row")
+    ap.add_argument("--e2e-eager", action="store_true", help="e2e: enqueue every step from Python instead of a graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the fused_step / graph_step context rows")
     args = ap.parse_args()
     if args.impl == "reference":
