@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""CTA timeline of one paged_attention_v1 launch (needs lib/libvllmini_b200_trace.so built with -DVB200_TRACE).
+"""CTA timeline of one paged_attention_v1 launch.  Needs a -DVB200_TRACE build of the library:
+
+    nvcc -shared -o vllmini_b200/lib/libvllmini_b200_trace.so -gencode arch=compute_100a,code=sm_100a -O3 \
+         -lineinfo -std=c++17 -Xcompiler -fPIC -DVB200_TRACE -Iinclude -Ivllmini_b200/csrc \
+         vllmini_b200/csrc/{abi,cache_kernels,cache_aux,paged_attention}.cu
 
 Prints where the launch's wall time goes: ramp-up, steady state, tail; per-CTA prologue and lifetime."""
 import ctypes
