@@ -32,6 +32,8 @@ CONFIGS = {
     "MIX": (256, 12, 64, 16, -2048),     # ctx ~ U[128, 2048] (BASELINE configs[2])
     "D128": (256, 8, 128, 16, 1024),
     "S1_8k": (1, 12, 64, 16, 8192),
+    "S1_48": (1, 12, 64, 16, 48),        # vllmini's own serving shape: 1 sequence, <= 64 tokens (server.py:37-50)
+    "S4_64": (4, 12, 64, 16, 64),
     "S1_1k": (1, 12, 64, 16, 1024),
     "S4_4k": (4, 12, 64, 16, 4096),
     "S16_512": (16, 12, 64, 16, 512),

@@ -12,6 +12,7 @@ static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_pdl{1};
 
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void disable_pdl() { g_pdl.store(0, std::memory_order_relaxed); }
 
 char* error_buffer() { return t_error; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

@@ -54,6 +54,7 @@ struct DeviceGuard {
 // kernel on the stream drains; every kernel calls griddep_wait() before it touches global memory, which blocks
 // until the previous kernel has completed and flushed (so stream-order semantics are unchanged).
 bool pdl_enabled();                // abi.cu (vb200_set_pdl)
+void disable_pdl();
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -68,7 +69,14 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e == cudaErrorNotSupported && cfg.numAttrs) {  // driver / capture mode without programmatic launches
+    cudaGetLastError();
+    disable_pdl();
+    cfg.numAttrs = 0;
+    e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  }
+  return e;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -18,7 +18,9 @@
 
 namespace {
 
-at::Tensor g_workspace[64];
+// Per-device workspace tensors.  Deliberately leaked: a static at::Tensor would be destroyed at interpreter
+// exit, possibly after torch's CUDA allocator is gone.
+at::Tensor* const g_workspace = new at::Tensor[64];
 
 void check_rc(int rc) {
   // reference: TORCH_CHECK -> c10::Error -> Python RuntimeError
