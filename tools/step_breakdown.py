@@ -33,6 +33,16 @@ def fused(l):
                                   hp.block_tables[l], hp.seq_lens, B, CTX)
 
 
+neg_slots = torch.full_like(hp.slots, -1)
+
+
+def fused_nostore(l):
+    """fused launch with every slot = -1 (padding): same code path, no row stores."""
+    q, k, v = hp.views(hp.qkv, l)
+    ops.paged_attention_v1_append(hp.out[l], q, k, v, hp.key_cache, hp.value_cache, neg_slots[l], H, hp.scale,
+                                  hp.block_tables[l], hp.seq_lens, B, CTX)
+
+
 def timed(fn, reps=30):
     for l in range(L):
         fn(l)
@@ -58,5 +68,6 @@ res = {
     "reshape_only_us_per_layer": timed(resh),
     "reshape_then_attention_us_per_layer": timed(lambda l: (resh(l), attn(l))),
     "fused_append_us_per_layer": timed(fused),
+    "fused_append_no_row_store_us_per_layer": timed(fused_nostore),
 }
 print(json.dumps(res))
