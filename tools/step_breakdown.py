@@ -43,6 +43,19 @@ def fused_nostore(l):
                                   hp.block_tables[l], hp.seq_lens, B, CTX)
 
 
+def fused_partial(frac):
+    """fused launch where only every `frac`-th sequence appends a row (the others carry slot -1)."""
+    sl = hp.slots.clone()
+    mask = (torch.arange(S, device=dev) % frac) != 0
+    sl[:, mask] = -1
+
+    def fn(l):
+        q, k, v = hp.views(hp.qkv, l)
+        ops.paged_attention_v1_append(hp.out[l], q, k, v, hp.key_cache, hp.value_cache, sl[l], H, hp.scale,
+                                      hp.block_tables[l], hp.seq_lens, B, CTX)
+    return fn
+
+
 def timed(fn, reps=30):
     for l in range(L):
         fn(l)
@@ -69,5 +82,8 @@ res = {
     "reshape_then_attention_us_per_layer": timed(lambda l: (resh(l), attn(l))),
     "fused_append_us_per_layer": timed(fused),
     "fused_append_no_row_store_us_per_layer": timed(fused_nostore),
+    "fused_append_every_2nd_seq_us_per_layer": timed(fused_partial(2)),
+    "fused_append_every_8th_seq_us_per_layer": timed(fused_partial(8)),
+    "fused_append_every_64th_seq_us_per_layer": timed(fused_partial(64)),
 }
 print(json.dumps(res))
