@@ -53,6 +53,8 @@ enum {
  * Replaces: paged_attention_v1(...) host entry, attention_kernels.cu:805-826, its launcher
  * :693-767 and kernel :86-527.
  *
+ *   head_size  64, 80, 96, 112, 128, 192 or 256 (the launcher's switch, :738-766); block_size 8, 16 or 32
+ *                (:789-803); anything else returns VB200_ERR_HEAD_SIZE / VB200_ERR_BLOCK_SIZE
  *   out        [num_seqs, num_heads, head_size] fp16, contiguous (written)
  *   query      [num_seqs, num_heads, head_size] fp16, row stride q_stride elements
  *   kv_block_stride = key_cache.stride(0), kv_head_stride = key_cache.stride(1); the same two

@@ -34,6 +34,20 @@ PARITY_CASES = [
     ("ctx512",           4, 12, 64, 16, 512, 14),                   # BASELINE configs[1] shape, fewer seqs
     ("ctx_mixed_long",   3, 12, 64, 16, (128, 1024, 2048), 15),     # BASELINE configs[2] range
     ("many_seqs_short",  64, 12, 64, 16, ("rand", 1, 80), 16),
+    # the reference launcher's other head sizes (attention_kernels.cu:738-766)
+    ("head80_bs8",       3, 4, 80, 8, (1, 50, 131), 17),            # partial last chunk per lane (80*8/8 = 80 chunks)
+    ("head80_bs16",      2, 4, 80, 16, (17, 140), 18),
+    ("head80_bs32",      2, 4, 80, 32, (33, 140), 19),
+    ("head96_bs8",       2, 4, 96, 8, (9, 99), 20),
+    ("head96_bs16",      2, 4, 96, 16, (16, 300), 21),
+    ("head112_bs8",      3, 2, 112, 8, (7, 64, 257), 22),           # partial last chunk per lane
+    ("head112_bs32",     2, 2, 112, 32, (31, 130), 23),
+    ("head192_bs8",      2, 2, 192, 8, (12, 150), 24),
+    ("head192_bs16",     2, 2, 192, 16, (40, 333), 25),
+    ("head192_bs32",     2, 2, 192, 32, (64, 200), 26),             # q kept in shared memory (24 chunks per lane)
+    ("head256_bs8",      2, 2, 256, 8, (3, 150), 27),
+    ("head256_bs16",     2, 2, 256, 16, (100, 513), 28),            # 3-warp CTA
+    ("head256_bs32",     2, 2, 256, 32, (95, 289), 29),             # q kept in shared memory (32 chunks per lane)
 ]
 
 

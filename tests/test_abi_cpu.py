@@ -69,7 +69,7 @@ def test_c_abi_argument_validation_without_gpu():
                                                 a["qs"], a["kbs"], a["khs"], 0.125, None, 0, 0, None)
     assert attn(block_size=4) == -2 and "Unsupported block size: 4" in _native.last_error()
     assert attn(block_size=64) == -2
-    assert attn(head_size=80) == -3 and "Unsupported head size: 80" in _native.last_error()
+    assert attn(head_size=72) == -3 and "Unsupported head size: 72" in _native.last_error()
     assert attn(num_heads=12, num_kv_heads=5) == -4
     assert attn(qs=770) == -4 and "stride" in _native.last_error()
     assert attn(num_seqs=0) == 0                       # empty batch is a no-op

@@ -50,7 +50,12 @@ def test_oracle_vs_reference_kernel_outputs(name, golden):
     rr = co.paged_attention_v1(*args, mode="ref_rounding")
     diff = np.abs(rr.astype(np.float64) - ref.astype(np.float64))
     assert (diff <= np.maximum(2 * _ulp16(ref), 1.3e-4)).all(), f"{name}: max {diff.max():.3e}"
-    assert (rr.view(np.uint16) == ref.view(np.uint16)).mean() >= 0.98
+    # A mismatch is always a whole (sequence, head) row nudged by an ex2.approx / rcp.approx ulp in its softmax
+    # normaliser, flipping ~10-20 % of that row's roundings; cases with only 4 rows (the large-head ones) are
+    # therefore allowed one such row.
+    same = (rr.view(np.uint16) == ref.view(np.uint16))
+    assert same.mean() >= (0.98 if case["S"] * case["H"] >= 16 else 0.94)
+    assert (~same).any(axis=-1).sum() <= max(1, int(0.3 * case["S"] * case["H"])), "too many perturbed rows"
     if int(case["sl"].max()) <= 40:
         assert np.array_equal(rr.view(np.uint16), ref.view(np.uint16)), "short contexts are bit-exact"
     # (2) the exact (fp64) oracle sits within the tolerance the parity tests use

@@ -468,7 +468,7 @@ def test_copy_blocks_and_swap_blocks_bit_exact(ref_ext):
 
 # ------------------------------------------------------------------------------ fused append + attend
 @pytest.mark.parametrize("self_attend", [True, False])
-@pytest.mark.parametrize("shape", ["batch", "long_small_batch", "gqa"])
+@pytest.mark.parametrize("shape", ["batch", "long_small_batch", "gqa", "head80_blk8", "head256_blk32"])
 def test_fused_append_equals_reshape_then_attention(self_attend, shape):
     """vb200_paged_attention_v1_append_f16 == reshape_and_cache followed by paged_attention_v1, bit for bit
     (same kernel arithmetic), for both position conventions: the new token attends to itself
@@ -481,6 +481,12 @@ def test_fused_append_equals_reshape_then_attention(self_attend, shape):
     elif shape == "long_small_batch":
         S, H, KVH, D, B = 2, 12, 12, 64, 16                 # split-KV path
         hist = np.array([3000, 2047])
+    elif shape == "head80_blk8":
+        S, H, KVH, D, B = 6, 4, 4, 80, 8                    # partial last chunk per lane
+        hist = np.array([0, 7, 8, 9, 63, 200])
+    elif shape == "head256_blk32":
+        S, H, KVH, D, B = 3, 4, 2, 256, 32                  # q in shared memory, 3-warp CTA
+        hist = np.array([0, 95, 300])
     else:
         S, H, KVH, D, B = 5, 8, 2, 128, 32
         hist = np.array([0, 31, 32, 33, 100])
@@ -515,7 +521,7 @@ def test_fused_append_equals_reshape_then_attention(self_attend, shape):
 
 # ------------------------------------------------------------------------------ randomized shapes
 def test_randomized_shapes_against_c_oracle():
-    """60 seeded random problems: batch 1..40, heads (MHA and GQA), head size 64/128, block 8/16/32, ragged
+    """60 seeded random problems: batch 1..40, heads (MHA and GQA), every head size, block 8/16/32, ragged
     lengths 0..700, padded tables, strided queries, random max_seq_len slack -- all against the fp64 oracle."""
     from vllmini_b200 import ops
     rng = np.random.default_rng(2024)
@@ -523,7 +529,7 @@ def test_randomized_shapes_against_c_oracle():
     dev = torch.device("cuda:0")
     worst = 0.0
     for trial in range(60):
-        D = int(rng.choice([64, 128]))
+        D = int(rng.choice([64, 128, 64, 80, 96, 112, 192, 256]))
         B = int(rng.choice([8, 16, 32]))
         KVH = int(rng.choice([1, 2, 4, 12]))
         H = KVH * int(rng.choice([1, 1, 2, 4]))

@@ -69,18 +69,30 @@ template <int D, int B, int W, int NST>
 struct PaCfg {
   static constexpr int BPS = 32 / B;             // KV blocks per 32-token stage
   static constexpr int TILE = D * B * 2;         // bytes of one (block, head) K tile (== V tile)
-  static constexpr int NJ = D * B / 256;         // 16-byte chunks per lane per tile
+  static constexpr int CH = D * B / 8;           // 16-byte chunks per tile
+  static constexpr int NJ = (CH + 31) / 32;      // chunks per lane per tile (the last one partial unless FULL)
+  static constexpr bool FULL = CH % 32 == 0;     // false only for head sizes 80 / 112 at block size 8
+  static constexpr bool QSMEM = NJ > 16;         // q stays in shared memory (head sizes 192 / 256 at block size 32)
+  static constexpr int NQ = QSMEM ? 1 : NJ;      // q chunks held in registers
   static constexpr int TPR = B / 8;              // 16-byte chunks per V row
   static constexpr int STAGE = 2 * BPS * TILE;   // bytes per stage: K tiles then V tiles (= 128*D)
   static constexpr int RING = W * NST * STAGE;
   static constexpr int PBUF_OFF = RING;                     // W * 32 halves
   static constexpr int BAR_OFF = PBUF_OFF + W * 64;         // W * NST mbarriers
   static constexpr int RED_OFF = BAR_OFF + W * NST * 8;     // W * (D + 2) floats
-  static constexpr int SMEM = RED_OFF + W * (D + 2) * 4;
+  static constexpr int Q_OFF = (RED_OFF + W * (D + 2) * 4 + 15) / 16 * 16;  // D halves (used when QSMEM)
+  static constexpr int SMEM = Q_OFF + D * 2;
   static constexpr int kD = D, kB = B;
   static_assert(B == 8 || B == 16 || B == 32, "block size");
-  static_assert(D % 8 == 0 && NJ >= 1 && (D * B) % 256 == 0, "head size");
+  static_assert(D % 16 == 0 && D >= 16 && D <= 256, "head size");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
 };
+
+// does chunk j of this lane exist in the tile?  (compile-time true except in the last chunk of a partial tile)
+template <class C>
+__device__ __forceinline__ bool chunk_ok(int lane, int j) {
+  return C::FULL || j < C::NJ - 1 || lane + 32 * j < C::CH;
+}
 
 // 8 fp16 x fp16 products accumulated in fp32 on two chains (FHFMA).
 __device__ __forceinline__ void dot8(const uint4& a, const uint4& b, float& c0, float& c1) {
@@ -114,10 +126,17 @@ __device__ __forceinline__ uint4 keep_first(uint4 v, int nv) {
 // 64-byte fp16 probability buffer.  Ends with a __syncwarp(): afterwards every lane is done with the
 // stage's shared memory and with pbuf.
 template <class C>
-__device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int lane, const uint4 (&qv)[C::NJ],
-                                              float& m, float& lsum, float (&acc)[C::NJ], int stage_tok0, int tok_end,
-                                              float scale_log2e) {
+__device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int lane, const uint4 (&qv)[C::NQ],
+                                              uint32_t qs, float& m, float& lsum, float (&acc)[C::NJ], int stage_tok0,
+                                              int tok_end, float scale_log2e) {
   constexpr int B = C::kB;
+  auto qchunk = [&](int j) -> uint4 {  // q dims 8*((lane + 32j)/B) .. +7
+    if constexpr (C::QSMEM) {
+      return lds128(qs + ((lane + 32 * j) / B) * 16);
+    } else {
+      return qv[j];
+    }
+  };
   // ---- QK^T: lane owns token lane % B of every block of the stage ----
   float part[C::BPS];
 #pragma unroll
@@ -125,8 +144,10 @@ __device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int
     float c0 = 0.f, c1 = 0.f;
 #pragma unroll
     for (int j = 0; j < C::NJ; ++j) {
-      const uint4 kv = lds128(sbase + b * C::TILE + (lane + 32 * j) * 16);
-      dot8(qv[j], kv, c0, c1);
+      if (chunk_ok<C>(lane, j)) {
+        const uint4 kv = lds128(sbase + b * C::TILE + (lane + 32 * j) * 16);
+        dot8(qchunk(j), kv, c0, c1);
+      }
     }
     part[b] = c0 + c1;
   }
@@ -177,15 +198,19 @@ __device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int
     if (!tail) {
 #pragma unroll
       for (int j = 0; j < C::NJ; ++j) {
-        const uint4 vv = lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16);
-        dot8(pv, vv, acc[j], c1[j]);
+        if (chunk_ok<C>(lane, j)) {
+          const uint4 vv = lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16);
+          dot8(pv, vv, acc[j], c1[j]);
+        }
       }
     } else {
       const int nv = tok_end - (stage_tok0 + b * B + (lane % C::TPR) * 8);
 #pragma unroll
       for (int j = 0; j < C::NJ; ++j) {
-        const uint4 vv = keep_first(lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16), nv);
-        dot8(pv, vv, acc[j], c1[j]);
+        if (chunk_ok<C>(lane, j)) {
+          const uint4 vv = keep_first(lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16), nv);
+          dot8(pv, vv, acc[j], c1[j]);
+        }
       }
     }
 #pragma unroll
@@ -225,7 +250,8 @@ __device__ __forceinline__ void warp_publish(float* red, int warp, int lane, flo
   }
   if (lane % C::TPR == 0) {
 #pragma unroll
-    for (int j = 0; j < C::NJ; ++j) red[warp * (D + 2) + lane / C::TPR + j * (32 / C::TPR)] = acc[j];
+    for (int j = 0; j < C::NJ; ++j)
+      if (chunk_ok<C>(lane, j)) red[warp * (D + 2) + lane / C::TPR + j * (32 / C::TPR)] = acc[j];
   }
   if (lane == 0) {
     red[warp * (D + 2) + D] = m;
@@ -426,11 +452,19 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   int next_phys = (warp + NST * W < nstages) ? load_phys(warp + NST * W) : 0;
 
   // ---- q: dims 8*(lane/B + j*BPS) .. +7 of this head's row, packed fp16 ----
-  uint4 qv[C::NJ];
+  uint4 qv[C::NQ];
+  const uint32_t qs = smem_u32(smem + C::Q_OFF);
   {
     const __half* qrow = p.q + (int64_t)seq * p.q_stride + (int64_t)head * D;
+    if constexpr (C::QSMEM) {  // large head x block: the row lives in shared memory, read per chunk (broadcast)
+      qv[0] = make_uint4(0, 0, 0, 0);
+      if (threadIdx.x < D / 8) *reinterpret_cast<uint4*>(smem + C::Q_OFF + threadIdx.x * 16) = ldg128(qrow + 8 * threadIdx.x);
+      __syncthreads();
+    } else {
 #pragma unroll
-    for (int j = 0; j < C::NJ; ++j) qv[j] = ldg128(qrow + 8 * (lane / B + j * C::BPS));
+      for (int j = 0; j < C::NJ; ++j)
+        qv[j] = chunk_ok<C>(lane, j) ? ldg128(qrow + 8 * (lane / B + j * C::BPS)) : make_uint4(0, 0, 0, 0);
+    }
   }
 
   float m = -INFINITY;  // running max (log2 domain), warp-uniform
@@ -465,7 +499,7 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
       }
       __syncwarp();
     }
-    process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, m, lsum, acc, r.tok_begin + st * 32, r.tok_end,
+    process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, qs, m, lsum, acc, r.tok_begin + st * 32, r.tok_end,
                      p.scale_log2e);
     // ---- refill this slot with the stage NST rounds ahead ----
     const int st_next = st + NST * W;
@@ -696,7 +730,7 @@ __global__ void __launch_bounds__((W + 1) * 32) pa_v1_persistent_kernel(const Pa
     for (int st = warp; st < U.nstages; st += W) {
       const int slot = n_consumed % NST;
       mbar_wait(bars + slot * 8, (n_consumed / NST) & 1);
-      process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, m, lsum, acc, U.tok_begin + st * 32, U.tok_end,
+      process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, 0u, m, lsum, acc, U.tok_begin + st * 32, U.tok_end,
                        p.scale_log2e);
       ++n_consumed;
       try_issue();
@@ -756,10 +790,13 @@ static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t str
   return VB200_OK;
 }
 
+// Default CTA shape per head size: 4 warps x 2 stages; head size 256 has 32 KB stages, three warps' rings fit.
+constexpr int default_warps(int head_size) { return head_size > 192 ? 3 : 4; }
+
 template <int D, int B, int W, int NST>
 static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
-  if (p.new_k != nullptr) {
-    if constexpr (W == 4 && NST == 2) return launch_classic_impl<D, B, 4, 2, true>(p, num_seqs, stream);
+  if (p.new_k != nullptr) {  // the fused append lives in the default instantiation of each head size
+    if constexpr (W == default_warps(D) && NST == 2) return launch_classic_impl<D, B, W, 2, true>(p, num_seqs, stream);
   }
   return launch_classic_impl<D, B, W, NST, false>(p, num_seqs, stream);
 }
@@ -813,15 +850,32 @@ static int launch_block(const PaParams& p, int num_seqs, int block_size, int var
   }
 }
 
+// The reference's other head sizes (attention_kernels.cu:738-766: 80, 96, 112, 192, 256): default shape only.
+template <int D>
+static int launch_block_default(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
+  constexpr int W = default_warps(D);
+  switch (block_size) {
+    case 8: return launch_classic<D, 8, W, 2>(p, num_seqs, stream);
+    case 16: return launch_classic<D, 16, W, 2>(p, num_seqs, stream);
+    case 32: return launch_classic<D, 32, W, 2>(p, num_seqs, stream);
+    default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
+  }
+}
+
+static bool head_size_supported(int d) {  // the reference launcher's switch, attention_kernels.cu:738-766
+  return d == 64 || d == 80 || d == 96 || d == 112 || d == 128 || d == 192 || d == 256;
+}
+static bool head_size_has_variants(int d) { return d == 64 || d == 128; }
+
 // split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
 // merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
 // is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
 static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq_len, int variant, int num_sms,
                          int* num_splits, int* split_tokens) {
-  (void)head_size;
   const Variant v = kVariants[variant];
   const int64_t base = (int64_t)num_seqs * num_heads;
-  const int quantum = 32 * v.W;  // tokens consumed by one round of the CTA's warps
+  const int warps = variant == 0 ? default_warps(head_size) : v.W;
+  const int quantum = 32 * warps;  // tokens consumed by one round of the CTA's warps
   const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
   if (g_tuning.force_splits > 0) {
@@ -858,9 +912,9 @@ using namespace vb200;
 extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
                                                            int32_t block_size, int32_t max_seq_len) {
   (void)block_size;
-  if (num_seqs <= 0 || num_heads <= 0 || (head_size != 64 && head_size != 128)) return 0;
+  if (num_seqs <= 0 || num_heads <= 0 || !head_size_supported(head_size)) return 0;
   int variant = g_tuning.variant;
-  if (variant < 0 || variant >= kNumVariants) variant = 0;
+  if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
   int ns = 1, st = 0;
   choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), &ns, &st);
   return workspace_bytes_for(num_seqs, num_heads, head_size, ns);
@@ -885,8 +939,7 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     return set_error(VB200_ERR_INVALID_ARGUMENT, "negative or zero size argument");
   if (block_size != 8 && block_size != 16 && block_size != 32)
     return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
-  if (head_size != 64 && head_size != 128)
-    return set_error(VB200_ERR_HEAD_SIZE, "Unsupported head size: %d", head_size);
+  if (!head_size_supported(head_size)) return set_error(VB200_ERR_HEAD_SIZE, "Unsupported head size: %d", head_size);
   if (num_heads % num_kv_heads != 0)
     return set_error(VB200_ERR_INVALID_ARGUMENT, "num_heads %d not a multiple of num_kv_heads %d", num_heads,
                      num_kv_heads);
@@ -906,7 +959,7 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   if (guard.status != cudaSuccess) return set_error(VB200_ERR_CUDA, "cudaSetDevice(%d): %s", device,
                                                      cudaGetErrorString(guard.status));
   int variant = g_tuning.variant;
-  if (variant < 0 || variant >= kNumVariants) variant = 0;
+  if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
 
   PaParams p;
   p.out = static_cast<__half*>(out);
@@ -954,8 +1007,15 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   }
   int* sched = static_cast<int*>(workspace);  // nullptr => static round-robin unit assignment
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_size == 64) return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
-  return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
+  switch (head_size) {
+    case 64: return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
+    case 128: return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
+    case 80: return launch_block_default<80>(p, num_seqs, block_size, s);
+    case 96: return launch_block_default<96>(p, num_seqs, block_size, s);
+    case 112: return launch_block_default<112>(p, num_seqs, block_size, s);
+    case 192: return launch_block_default<192>(p, num_seqs, block_size, s);
+    default: return launch_block_default<256>(p, num_seqs, block_size, s);
+  }
 }
 
 extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache,
