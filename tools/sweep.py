@@ -31,6 +31,13 @@ CONFIGS = {
     "L8k_b32": (256, 20, 64, 32, 8192),
     "MIX": (256, 12, 64, 16, -2048),     # ctx ~ U[128, 2048] (BASELINE configs[2])
     "D128": (256, 8, 128, 16, 1024),
+    "D80": (256, 8, 80, 16, 1024),       # the reference launcher's other head sizes
+    "D96": (256, 8, 96, 16, 1024),
+    "D112": (256, 8, 112, 16, 1024),
+    "D192": (256, 4, 192, 16, 1024),
+    "D256": (256, 4, 256, 16, 1024),
+    "D80_b8": (256, 8, 80, 8, 1024),
+    "D256_b32": (256, 4, 256, 32, 1024),
     "S1_8k": (1, 12, 64, 16, 8192),
     "S1_48": (1, 12, 64, 16, 48),        # vllmini's own serving shape: 1 sequence, <= 64 tokens (server.py:37-50)
     "S4_64": (4, 12, 64, 16, 64),

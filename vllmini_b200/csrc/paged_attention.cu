@@ -85,7 +85,7 @@ struct PaCfg {
   static constexpr int kD = D, kB = B;
   static_assert(B == 8 || B == 16 || B == 32, "block size");
   static_assert(D % 16 == 0 && D >= 16 && D <= 256, "head size");
-  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static constexpr bool FITS = SMEM <= 227 * 1024;
 };
 
 // does chunk j of this lane exist in the tile?  (compile-time true except in the last chunk of a partial tile)
@@ -765,7 +765,7 @@ struct Variant {
   int W, NST;
   bool persistent;
 };
-// 0 (default): classic grid (H, S, splits), 4 warps x 2 stages; 1: classic 4x3; 2: classic 8x1; 3: classic 2x2;
+// 0 (default): classic grid (H, S, splits), default_warps(D) warps x 2 stages; 1: classic 4x3; 2: classic 8x1; 3: classic 2x2;
 // 4: persistent 4x2 (+1 scheduler warp); 5: persistent 8x1; 6: persistent 4x3; 7: persistent 2x2.
 // The persistent variants are kept for experiments: on B200 they measured 3-8 % SLOWER than the classic
 // grid at every BASELINE shape (profiles/r01c_persistent_vs_classic.md), so they are not the default.
@@ -776,6 +776,7 @@ constexpr int kNumVariants = 8;
 template <int D, int B, int W, int NST, bool APPEND>
 static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
   using C = PaCfg<D, B, W, NST>;
+  static_assert(C::FITS, "shared memory");
   auto kern = pa_v1_kernel<D, B, W, NST, APPEND>;
   static bool attr_set[64] = {};
   int dev = 0;
@@ -790,8 +791,12 @@ static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t str
   return VB200_OK;
 }
 
-// Default CTA shape per head size: 4 warps x 2 stages; head size 256 has 32 KB stages, three warps' rings fit.
-constexpr int default_warps(int head_size) { return head_size > 192 ? 3 : 4; }
+// Default CTA shape per head size: W warps x 2 stages of 128*D bytes, W chosen so that the resident CTAs of an SM
+// keep the most bytes in flight within 227 KB (measured, profiles/r01j_head_sizes.md): 4 warps at 64 (3 CTAs/SM),
+// 96 (2) and 192 (1); 3 warps at 80 (3), 112 (2), 128 (2) and 256 (1).
+constexpr int default_warps(int head_size) {
+  return (head_size == 64 || head_size == 96 || head_size == 192) ? 4 : 3;
+}
 
 template <int D, int B, int W, int NST>
 static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
@@ -835,7 +840,7 @@ static int launch_variant(const PaParams& p, int num_seqs, int variant, int* sch
     case 5: return launch_persistent<D, B, 8, 1>(p, num_seqs, sched, stream);
     case 6: return launch_persistent<D, B, 4, 3>(p, num_seqs, sched, stream);
     case 7: return launch_persistent<D, B, 2, 2>(p, num_seqs, sched, stream);
-    default: return launch_classic<D, B, 4, 2>(p, num_seqs, stream);
+    default: return launch_classic<D, B, default_warps(D), 2>(p, num_seqs, stream);
   }
 }
 
@@ -851,15 +856,22 @@ static int launch_block(const PaParams& p, int num_seqs, int block_size, int var
 }
 
 // The reference's other head sizes (attention_kernels.cu:738-766: 80, 96, 112, 192, 256): default shape only.
+template <int D, int W, int NST>
+static int launch_block_shape(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
+  if constexpr (PaCfg<D, 16, W, NST>::FITS) {
+    switch (block_size) {
+      case 8: return launch_classic<D, 8, W, NST>(p, num_seqs, stream);
+      case 16: return launch_classic<D, 16, W, NST>(p, num_seqs, stream);
+      case 32: return launch_classic<D, 32, W, NST>(p, num_seqs, stream);
+      default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
+    }
+  } else {
+    return set_error(VB200_ERR_UNSUPPORTED, "shape %dx%d does not fit at head size %d", W, NST, D);
+  }
+}
 template <int D>
 static int launch_block_default(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
-  constexpr int W = default_warps(D);
-  switch (block_size) {
-    case 8: return launch_classic<D, 8, W, 2>(p, num_seqs, stream);
-    case 16: return launch_classic<D, 16, W, 2>(p, num_seqs, stream);
-    case 32: return launch_classic<D, 32, W, 2>(p, num_seqs, stream);
-    default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
-  }
+  return launch_block_shape<D, default_warps(D), 2>(p, num_seqs, block_size, stream);
 }
 
 static bool head_size_supported(int d) {  // the reference launcher's switch, attention_kernels.cu:738-766
