@@ -346,8 +346,8 @@ class HostDrivenStep:
 
 
 def run_full_model(args, dev, world, rank):
-    """Whole GPT-2 small decode step (cuBLAS GEMMs + LayerNorm + GELU via torch, the two hot ops via
-    the binding) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
+    """Whole GPT-2 small decode step (cuBLAS GEMMs + GELU via torch; the hot ops, residual-add+LayerNorm
+    and argmax via the library) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
     driver of SURVEY.md 8f rank 1), CUDA-graph replayed.  Reported as context next to the hot-path
     `value`; at N>1 rank 0's weights are broadcast over NCCL first (the path's only collective)."""
     import numpy as np
@@ -412,7 +412,9 @@ def run_full_model(args, dev, world, rank):
             "model": "GPT-2 small (12 layers, 12x64 heads, vocab 50257), synthetic seeded weights, fp16",
             "ctx": f"{CTX}..{CTX + steps + 4} (grows one token per step)",
             "how": "vllmini_b200.decode: batched block bookkeeping on host (no D2H sync), whole step in one CUDA "
-                   "graph (torch/cuBLAS GEMMs + LayerNorm + GELU + the two hot-path kernels per layer + argmax)",
+                   "graph: per layer 4 cuBLAS GEMMs + GELU (torch), the fused append+attention launch and two fused "
+                   "residual-add+LayerNorm launches (own kernels); lm_head on the 64-row-padded tied embedding; "
+                   "own row-argmax",
             "weight_broadcast_s": t_bcast, "setup_s": time.perf_counter() - t0}
 
 

@@ -137,6 +137,27 @@ int vb200_reshape_and_cache_flash_f16(const void* key, const void* value, void* 
                                       int32_t head_size, int32_t block_size, int64_t block_stride, int64_t key_stride,
                                       int64_t value_stride, int32_t device, void* stream);
 
+/*
+ * Residual add + LayerNorm for the batched decode driver (vllmini_b200/decode.py; not part of the reference's
+ * extension -- in vllmini these are eager torch ops between the two hot-path calls, gpt2.py:150-160, 258-262):
+ *
+ *   s          = fp16(a[ar] + x[xr])             ar = a_rows ? a_rows[r] : r,  xr = x_rows ? x_rows[r] : r
+ *   x_out[r]   = s                                [num_rows, hidden] contiguous; may alias x when x_rows is NULL
+ *   ln_out[r]  = fp16((s - mean(s)) * rsqrt(var(s) + eps) * gamma + beta)     statistics in fp32
+ *
+ * a, x: fp16 rows of `hidden` elements, row strides a_stride / x_stride (elements); hidden % 8 == 0, <= 2048.
+ * With a = wte, a_rows = token ids, x = wpe, x_rows = positions it is the embedding step.
+ */
+int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a, const int64_t* a_rows, int64_t a_stride,
+                            const void* x, const int64_t* x_rows, int64_t x_stride, const void* gamma,
+                            const void* beta, int32_t num_rows, int32_t hidden, float eps, int32_t device,
+                            void* stream);
+
+/* Greedy sampling for the decode driver: out[r] = argmax over x[r, 0..n) (fp16 rows, row_stride elements apart);
+ * first index among equal maxima, NaN counts as the maximum (torch.argmax semantics). */
+int vb200_argmax_rows_f16(int64_t* out, const void* x, int64_t row_stride, int32_t num_rows, int32_t n,
+                          int32_t device, void* stream);
+
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* vb200_last_error(void);
 

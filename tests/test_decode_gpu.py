@@ -20,7 +20,7 @@ def _load(name):
 
 def _run(shape, seed, prompts, new_tokens, use_graph, max_seqs=None, dtype=torch.float16, fused=True):
     dev = torch.device("cuda:0")
-    model = GPT2Decoder(shape, dev, dtype=dtype, fused_append=fused)
+    model = GPT2Decoder(shape, dev, dtype=dtype, fused_append=fused, fused_layernorm=fused)
     model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=seed))
     B, MB = 16, 4
     S = max_seqs or len(prompts)
@@ -65,7 +65,8 @@ def test_greedy_decode_matches_reference_model_golden(name, use_graph, batched):
     if batched:      # other sequences of different lengths in the same batch must not change row 0
         prompts += [rng.integers(0, shape.vocab_size, size=n).tolist() for n in (3, 16, 17, 30)]
     toks, rows = _run(shape, int(g["seed"]), prompts, len(g["tokens"]), use_graph, max_seqs=len(prompts) + 1,
-                      fused=use_graph)      # graph runs use the fused append+attend launch, eager runs the two calls
+                      fused=use_graph)      # graph runs use the fused launches (append+attend, add+LayerNorm),
+    #                                         eager runs the reference's two calls and plain torch ops
     tol = 0.06       # fp16 weights/activations vs the reference model in fp32 on CPU
     for step, row in enumerate(rows):
         want_v, want_i = g["top_vals"][step], g["top_ids"][step]
@@ -112,3 +113,75 @@ def test_greedy_generate_harness_and_block_growth():
         assert kv.h_lens.tolist() == [1 + 39, 15 + 39, 16 + 39, 33 + 39]
     agree = np.mean([a == b for ra, rb in zip(*outs) for a, b in zip(ra, rb)])
     assert agree > 0.9          # identical arithmetic; near-ties may flip under different split factors
+
+
+@pytest.mark.parametrize("rows,hidden", [(1, 64), (5, 768), (256, 768), (33, 1024), (7, 1600), (3, 2048)])
+@pytest.mark.parametrize("gather", [False, True])
+def test_add_layernorm_matches_torch_fp32_reference(rows, hidden, gather):
+    """ops.add_layernorm against the same arithmetic in plain torch fp32: the residual sum is rounded to fp16
+    first (it is stored in fp16), LayerNorm statistics in fp32.  Tolerance: 1 fp16 ulp of the output (|y| <~ 8)
+    for ln_out; x_out bit-exact."""
+    from vllmini_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(rows * 10007 + hidden)
+    gamma = (1 + 0.1 * torch.randn(hidden, generator=g, device=dev)).half()
+    beta = (0.1 * torch.randn(hidden, generator=g, device=dev)).half()
+    if gather:          # the embedding step: a = table[ids], x = table2[pos]; row stride wider than hidden
+        table = torch.randn(97, hidden + 8, generator=g, device=dev).half()[:, :hidden]
+        table2 = torch.randn(50, hidden, generator=g, device=dev).half()
+        ia = torch.randint(0, 97, (rows,), generator=g, device=dev)
+        ix = torch.randint(0, 50, (rows,), generator=g, device=dev)
+        a_src, x_src, a_eff, x_eff = table, table2, table[ia], table2[ix]
+        x_out = torch.empty(rows, hidden, dtype=torch.float16, device=dev)
+    else:
+        a_src = a_eff = torch.randn(rows, hidden, generator=g, device=dev).half()
+        x_src = torch.randn(rows, hidden, generator=g, device=dev).half() * 3
+        x_eff = x_src.clone()
+        ia = ix = None
+        x_out = x_src                                                # in place
+    ln_out = torch.empty(rows, hidden, dtype=torch.float16, device=dev)
+    want_x = (a_eff.float() + x_eff.float()).half()
+    want_ln = torch.nn.functional.layer_norm(want_x.float(), (hidden,), gamma.float(), beta.float(), 1e-5)
+    ops.add_layernorm(a_src, x_src, gamma, beta, 1e-5, x_out, ln_out, a_rows=ia, x_rows=ix)
+    torch.cuda.synchronize()
+    assert torch.equal(x_out, want_x)
+    err = (ln_out.float() - want_ln).abs()
+    assert bool((err <= 2.0 ** -10 * want_ln.abs() + 1e-3).all()), f"max err {err.max().item():.3e}"
+
+
+def test_fused_layernorm_decode_matches_plain_torch_decode():
+    """The decoder with fused add+LayerNorm launches (and the padded lm_head) gives the same logits as the one
+    built from plain torch ops, on the same fp16 weights."""
+    g, shape = _load("gpt2_greedy_small")
+    dev = torch.device("cuda:0")
+    sd = synthetic_gpt2_state_dict(shape, seed=3)
+    rng = np.random.default_rng(4)
+    prompts = [rng.integers(0, shape.vocab_size, size=n).tolist() for n in (5, 16, 23)]
+    logits = []
+    for fused in (False, True):
+        model = GPT2Decoder(shape, dev, fused_layernorm=fused)
+        model.load_state_dict(sd)
+        kv = BatchedKVState(shape.n_layer * 3 * 4, shape.n_layer, shape.n_head, shape.head_size, 16, 3, 4, dev)
+        for i, pr in enumerate(prompts):
+            model.prefill(torch.tensor(pr, dtype=torch.int64, device=dev), kv, i)
+        kv.begin_decode_step()
+        ids = torch.tensor([11, 22, 33], dtype=torch.int64, device=dev)
+        lg = model.decode_forward(ids, torch.from_numpy(kv.positions()).to(dev), kv)
+        assert lg.shape == (3, shape.vocab_size)
+        logits.append(lg.float())
+    assert (logits[0] - logits[1]).abs().max().item() < 0.02
+
+
+def test_argmax_rows_matches_torch():
+    from vllmini_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(9)
+    for rows, n, pad in ((1, 7, 0), (3, 503, 1), (256, 50257, 47), (5, 4096, 0)):
+        x = torch.randn(rows, n + pad, generator=g, device=dev).half()[:, :n]
+        x[0, n // 2] = x[0, n - 1] = 60000.0                  # tie: first index wins
+        assert torch.equal(ops.argmax_rows(x), torch.argmax(x, dim=-1)), (rows, n)
+    x = torch.randn(4, 100, generator=g, device=dev).half()
+    x[2, 17] = x[2, 60] = float("nan")
+    x[1, :] = float("-inf")
+    x[3, :50] = float("-inf")
+    assert torch.equal(ops.argmax_rows(x), torch.argmax(x, dim=-1))

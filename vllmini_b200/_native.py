@@ -29,6 +29,8 @@ SYMBOLS = {
     "vb200_swap_blocks": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vb200_reshape_and_cache_flash_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64,
                                                  _i32, _vp]),
+    "vb200_add_layernorm_f16": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
+    "vb200_argmax_rows_f16": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "vb200_last_error": (ctypes.c_char_p, []),
     "vb200_abi_version": (_i32, []),
     "vb200_launch_count": (ctypes.c_uint64, []),

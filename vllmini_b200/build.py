@@ -18,7 +18,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvllmini_b200.so")
-SOURCES = ["abi.cu", "cache_kernels.cu", "cache_aux.cu", "paged_attention.cu"]
+SOURCES = ["abi.cu", "cache_kernels.cu", "cache_aux.cu", "model_aux.cu", "paged_attention.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "vllmini_b200.h")]
 
 

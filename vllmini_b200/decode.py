@@ -195,10 +195,14 @@ class GPT2Decoder:
     Parameter names and shapes are the reference GPT2LMHeadModel's (nn.Linear [out, in] weights,
     exact-erf GELU as gpt2.py:123), so `load_state_dict` accepts a reference state_dict."""
 
-    def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16, fused_append: bool = True):
+    def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16, fused_append: bool = True,
+                 fused_layernorm: bool = True):
         self.shape, self.device, self.dtype = shape, device, dtype
         # decode: one fused launch per layer (scatter + attention) instead of the reference's two calls
         self.fused_append = fused_append
+        # decode: residual add + LayerNorm (and the embedding sum + ln_1) as one launch each instead of two
+        # eager torch kernels; False keeps plain torch ops (the test reference for the fused path)
+        self.fused_layernorm = fused_layernorm and dtype is torch.float16
         self.w: Dict[str, torch.Tensor] = {}
         self.scale = shape.head_size ** -0.5
         self._graph = None
@@ -208,6 +212,12 @@ class GPT2Decoder:
         self.w = {k: v.detach().to(device=self.device, dtype=self.dtype).contiguous() for k, v in sd.items()
                   if k != "lm_head.weight"}
         self.w["lm_head.weight"] = self.w["transformer.wte.weight"]
+        # decode-time lm_head operand: the tied embedding padded to a multiple of 64 rows.  vocab 50257 is odd, so
+        # the [S, E] x [E, V] GEMM has an unaligned leading dimension and cuBLAS falls back to a legacy kernel
+        # (182 us vs ~30 us at S=256); the zero rows only add logits that are sliced away again.
+        V, E = self.w["lm_head.weight"].shape
+        self._lm_head_padded = torch.zeros(((V + 63) // 64 * 64, E), dtype=self.dtype, device=self.device)
+        self._lm_head_padded[:V].copy_(self.w["lm_head.weight"])
         self._graph = None
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -259,24 +269,63 @@ class GPT2Decoder:
         paged_attention_v1 (gpt2.py:44, 62)."""
         s = self.shape
         S = input_ids.numel()
-        H, D, B = s.n_head, s.head_size, kv.block_size
-        max_seq_len = kv.max_blocks_per_seq * B                       # capacity, as scheduler.py:97
+        if self.fused_layernorm:
+            return self._decode_forward_fused(input_ids, position_ids, kv)
         x = self.w["transformer.wte.weight"][input_ids] + self.w["transformer.wpe.weight"][position_ids]
         for i in range(s.n_layer):
             p = f"transformer.h.{i}."
             qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
-            q, k, v = (t.view(S, H, D) for t in qkv.split(s.n_embd, dim=-1))
-            o = torch.empty((S, H, D), dtype=self.dtype, device=self.device)
-            if self.fused_append:
-                ops.paged_attention_v1_append(o, q, k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], H, self.scale,
-                                              kv.d_tables[i], kv.d_lens, B, max_seq_len)
-            else:
-                ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[i], "auto", 1.0)
-                ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[i], kv.d_lens,
-                                       B, max_seq_len, None, "auto", 1.0, 0, 0, 1, 1, 0)
+            o = self._decode_attention(qkv, kv, i)
             x = x + F.linear(o.view(S, s.n_embd), self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
             x = x + self._mlp(self._ln(x, p + "ln_2"), p)
-        return F.linear(self._ln(x, "transformer.ln_f"), self.w["lm_head.weight"])
+        return self._lm_head(self._ln(x, "transformer.ln_f"))
+
+    def _decode_attention(self, qkv: torch.Tensor, kv: BatchedKVState, layer: int) -> torch.Tensor:
+        """The hot path of one layer: reshape_and_cache + paged_attention_v1 (gpt2.py:44, 62), or their fusion."""
+        s = self.shape
+        S = qkv.shape[0]
+        H, D, B = s.n_head, s.head_size, kv.block_size
+        max_seq_len = kv.max_blocks_per_seq * B                       # capacity, as scheduler.py:97
+        q, k, v = (t.view(S, H, D) for t in qkv.split(s.n_embd, dim=-1))
+        o = torch.empty((S, H, D), dtype=self.dtype, device=self.device)
+        if self.fused_append:
+            ops.paged_attention_v1_append(o, q, k, v, kv.key_cache, kv.value_cache, kv.d_slots[layer], H, self.scale,
+                                          kv.d_tables[layer], kv.d_lens, B, max_seq_len)
+        else:
+            ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[layer], "auto", 1.0)
+            ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[layer], kv.d_lens,
+                                   B, max_seq_len, None, "auto", 1.0, 0, 0, 1, 1, 0)
+        return o
+
+    def _lm_head(self, h: torch.Tensor) -> torch.Tensor:
+        return F.linear(h, self._lm_head_padded)[:, : self.shape.vocab_size]
+
+    def _decode_forward_fused(self, input_ids: torch.Tensor, position_ids: torch.Tensor, kv: BatchedKVState):
+        """Same arithmetic with every `x = x + y; h = LayerNorm(x)` pair (and the embedding sum + ln_1) done by
+        ops.add_layernorm: 8 launches per layer instead of 10."""
+        s, w = self.shape, self.w
+        S, E, eps = input_ids.numel(), s.n_embd, s.layer_norm_epsilon
+        x = torch.empty((S, E), dtype=self.dtype, device=self.device)
+        h = torch.empty((S, E), dtype=self.dtype, device=self.device)
+        ops.add_layernorm(w["transformer.wte.weight"], w["transformer.wpe.weight"], w["transformer.h.0.ln_1.weight"],
+                          w["transformer.h.0.ln_1.bias"], eps, x, h, a_rows=input_ids, x_rows=position_ids)
+        for i in range(s.n_layer):
+            p = f"transformer.h.{i}."
+            nxt = f"transformer.h.{i + 1}.ln_1" if i + 1 < s.n_layer else "transformer.ln_f"
+            qkv = F.linear(h, w[p + "attn.c_attn.weight"], w[p + "attn.c_attn.bias"])
+            o = self._decode_attention(qkv, kv, i)
+            a = F.linear(o.view(S, E), w[p + "attn.c_proj.weight"], w[p + "attn.c_proj.bias"])
+            ops.add_layernorm(a, x, w[p + "ln_2.weight"], w[p + "ln_2.bias"], eps, x, h)
+            a = F.linear(F.gelu(F.linear(h, w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"])),
+                         w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"])
+            ops.add_layernorm(a, x, w[nxt + ".weight"], w[nxt + ".bias"], eps, x, h)
+        return self._lm_head(h)
+
+    def greedy(self, logits: torch.Tensor) -> torch.Tensor:
+        """argmax over the vocabulary (one launch of the library's row-argmax when the fused helpers are on)."""
+        if self.fused_layernorm and logits.dtype is torch.float16:
+            return ops.argmax_rows(logits)
+        return torch.argmax(logits, dim=-1)
 
     # -- CUDA-graph capture of the decode step -----------------------------------------------------
     def capture_decode_graph(self, kv: BatchedKVState) -> None:
@@ -296,7 +345,7 @@ class GPT2Decoder:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self.g_logits = self.decode_forward(self.g_ids, self.g_pos, kv)
-            self.g_next = torch.argmax(self.g_logits, dim=-1)
+            self.g_next = self.greedy(self.g_logits)
 
     def replay_decode_graph(self) -> torch.Tensor:
         self._graph.replay()
@@ -330,7 +379,7 @@ def greedy_generate(model: GPT2Decoder, kv: BatchedKVState, prompts: Sequence[Se
             model.g_pos.copy_(pos)
             cur = model.replay_decode_graph().clone()
         else:
-            cur = torch.argmax(model.decode_forward(cur, pos, kv), dim=-1)
+            cur = model.greedy(model.decode_forward(cur, pos, kv))
         out.append(cur)
     ids = torch.stack(out, dim=1)[:n].cpu().tolist()
     return ids

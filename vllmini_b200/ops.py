@@ -217,6 +217,58 @@ def paged_attention_v1_append(
     _check(rc)
 
 
+def add_layernorm(a: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                  x_out: torch.Tensor, ln_out: torch.Tensor, a_rows: Optional[torch.Tensor] = None,
+                  x_rows: Optional[torch.Tensor] = None) -> None:
+    """Decode-driver helper (no reference counterpart; vllmini does this with eager torch ops, gpt2.py:150-160):
+    x_out = fp16(a[a_rows] + x[x_rows]); ln_out = LayerNorm(x_out) * gamma + beta, one launch.  `x_out` may be `x`
+    itself (in place) when x_rows is None.  a, x: [*, hidden] fp16 with contiguous rows; x_out, ln_out
+    [num_rows, hidden] contiguous; a_rows / x_rows: optional int64 row indices (the embedding lookup)."""
+    for t, name in ((a, "a"), (x, "x"), (gamma, "gamma"), (beta, "beta"), (x_out, "x_out"), (ln_out, "ln_out")):
+        _require_cuda(t, name)
+        if t.dtype is not torch.float16:
+            raise RuntimeError(f"vllmini_b200: {name} must be float16")
+    hidden = x_out.shape[-1]
+    num_rows = x_out.numel() // hidden
+    if a.dim() != 2 or x.dim() != 2 or a.stride(1) != 1 or x.stride(1) != 1 or a.shape[1] != hidden or x.shape[1] != hidden:
+        raise RuntimeError("vllmini_b200: a and x must be [rows, hidden] with contiguous rows")
+    if not (x_out.is_contiguous() and ln_out.is_contiguous() and gamma.is_contiguous() and beta.is_contiguous()) \
+            or ln_out.numel() != x_out.numel() or gamma.numel() != hidden or beta.numel() != hidden:
+        raise RuntimeError("vllmini_b200: x_out/ln_out must be contiguous [num_rows, hidden], gamma/beta [hidden]")
+    for rows, src, name in ((a_rows, a, "a_rows"), (x_rows, x, "x_rows")):
+        if rows is None:
+            if src.shape[0] < num_rows:
+                raise RuntimeError(f"vllmini_b200: fewer source rows than num_rows and no {name}")
+        else:
+            _require_cuda(rows, name)
+            if rows.dtype is not torch.int64 or not rows.is_contiguous() or rows.numel() != num_rows:
+                raise RuntimeError(f"vllmini_b200: {name} must be a contiguous int64 tensor of num_rows entries")
+    dev = x_out.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    rc = _native.load().vb200_add_layernorm_f16(
+        x_out.data_ptr(), ln_out.data_ptr(), a.data_ptr(), a_rows.data_ptr() if a_rows is not None else None,
+        a.stride(0), x.data_ptr(), x_rows.data_ptr() if x_rows is not None else None, x.stride(0),
+        gamma.data_ptr(), beta.data_ptr(), num_rows, hidden, float(eps), dev_index,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
+
+
+def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode-driver helper: torch.argmax(x, dim=-1) for fp16 logits [rows, n] (rows may be strided), one launch."""
+    _require_cuda(x, "x")
+    if x.dtype is not torch.float16 or x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError("vllmini_b200: x must be a float16 [rows, n] tensor with contiguous rows")
+    if out is None:
+        out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    elif out.dtype is not torch.int64 or not out.is_contiguous() or out.numel() != x.shape[0] or out.device != x.device:
+        raise RuntimeError("vllmini_b200: out must be a contiguous int64 tensor of `rows` entries on x's device")
+    dev = x.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    _check(_native.load().vb200_argmax_rows_f16(out.data_ptr(), x.data_ptr(), x.stride(0), x.shape[0], x.shape[1],
+                                                dev_index, torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
 # ---- binding selection -------------------------------------------------------------------------------
 # The two functions above bind the C ABI through ctypes (no build dependency on torch).  When the compiled
 # torch shim (csrc/torch_shim.cpp -> _torch_shim*.so, `python -m vllmini_b200.build`) is present it replaces
