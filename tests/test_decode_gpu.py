@@ -185,3 +185,33 @@ def test_argmax_rows_matches_torch():
     x[1, :] = float("-inf")
     x[3, :50] = float("-inf")
     assert torch.equal(ops.argmax_rows(x), torch.argmax(x, dim=-1))
+
+
+def test_async_step_publishing_ring_never_tears():
+    """begin_decode_step stages slots / lens / positions / new blocks through a ring of pinned buffers with no
+    host-device sync; running far ahead of the GPU must still give every step its own values.  A CPU twin of
+    the same state machine supplies the expectations."""
+    dev = torch.device("cuda:0")
+    L, S, MB, B = 3, 37, 12, 4
+
+    def make(device):
+        kv = BatchedKVState(L * S * MB, L, 2, 8, B, S, MB, device)
+        rng = np.random.default_rng(0)
+        for s_ in range(S):
+            if s_ % 5 != 4:
+                kv.add_sequence(s_, int(rng.integers(1, 9)))
+        return kv
+
+    gpu, cpu = make(dev), make(torch.device("cpu"))
+    slow = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    snaps, want = [], []
+    for step in range(30):
+        slow.normal_()                                   # keep the GPU busy so that the host runs ahead
+        gpu.begin_decode_step()
+        cpu.begin_decode_step()
+        snaps.append((gpu.d_slots.clone(), gpu.d_lens.clone(), gpu.d_pos.clone(), gpu.d_tables.clone()))
+        want.append((cpu.d_slots.clone(), cpu.d_lens.clone(), cpu.d_pos.clone(), cpu.d_tables.clone()))
+    torch.cuda.synchronize()
+    for step, (got, exp) in enumerate(zip(snaps, want)):
+        for g_, e_ in zip(got, exp):
+            assert torch.equal(g_.cpu(), e_), f"step {step}"

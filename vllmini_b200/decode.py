@@ -77,10 +77,25 @@ class BatchedKVState:
         self.d_tables = torch.full((num_layers, max_seqs, max_blocks_per_seq), -1, dtype=torch.int32, device=device)
         self.d_lens = torch.zeros(max_seqs, dtype=torch.int32, device=device)       # seq_lens passed to attention
         self.d_slots = torch.full((num_layers, max_seqs), -1, dtype=torch.int64, device=device)
-        self._pin_slots = torch.empty((num_layers, max_seqs), dtype=torch.int64).pin_memory() \
-            if device.type == "cuda" else torch.empty((num_layers, max_seqs), dtype=torch.int64)
-        self._pin_lens = torch.empty(max_seqs, dtype=torch.int32).pin_memory() \
-            if device.type == "cuda" else torch.empty(max_seqs, dtype=torch.int32)
+        self.d_pos = torch.zeros(max_seqs, dtype=torch.int64, device=device)       # position ids of the new tokens
+        # Per-step host->device staging: ONE packed pinned buffer [slots int64 | positions int64 | new-block
+        # (seq, column) int64 pairs | lens int32 | new block ids int32] and one async copy per step.  A ring of
+        # buffers, each guarded by an event recorded after its copy, lets the host prepare step t+1 .. t+RING-1
+        # while the GPU still runs step t (nothing on the step path synchronises the host with the device).
+        L, S = num_layers, max_seqs
+        self._o_pos = L * S * 8
+        self._o_grow = self._o_pos + S * 8
+        self._o_lens = self._o_grow + 2 * S * 8
+        self._o_blocks = self._o_lens + S * 4
+        self._stage_bytes = self._o_blocks + L * S * 4
+        self._ring = []
+        for _ in range(4):
+            buf = torch.empty(self._stage_bytes, dtype=torch.uint8)
+            if device.type == "cuda":
+                buf = buf.pin_memory()
+            self._ring.append([buf, torch.cuda.Event() if device.type == "cuda" else None, False])
+        self._ring_i = 0
+        self._d_stage = torch.empty(self._stage_bytes, dtype=torch.uint8, device=device)
 
     # -- allocation ---------------------------------------------------------------------------
     def _take(self, n: int) -> List[int]:
@@ -128,28 +143,54 @@ class BatchedKVState:
         seq_lens = L after writing slot L, scheduler.py:96-101, so the new token does not attend to
         itself); True attends over L + 1 tokens like ordinary causal decoding."""
         B = self.block_size
+        L, S = self.num_layers, self.max_seqs
         act = np.nonzero(self.active)[0]
         pos = self.h_lens[act].astype(np.int64)                    # position of the new token
         if (pos >= self.max_blocks_per_seq * B).any():
             raise RuntimeError("sequence exceeds max_blocks_per_seq * block_size")
+        # next staging buffer of the ring; wait (host side) only if the GPU is a whole ring behind
+        buf, ev, used = self._ring[self._ring_i]
+        if used and ev is not None:
+            ev.synchronize()
+        hb = buf.numpy()
+        h_slots = hb[: self._o_pos].view(np.int64).reshape(L, S)
+        h_pos = hb[self._o_pos: self._o_grow].view(np.int64)
+        h_grow = hb[self._o_grow: self._o_lens].view(np.int64).reshape(2, S)
+        h_lens = hb[self._o_lens: self._o_blocks].view(np.int32)
+        h_blocks = hb[self._o_blocks:].view(np.int32).reshape(L, S)
+
         need = act[pos % B == 0]                                    # last block full (or empty): append one
         if need.size:
             idx = (self.h_lens[need] // B).astype(np.int64)
-            new_blocks = np.asarray(self._take(need.size * self.num_layers), dtype=np.int32)
-            new_blocks = new_blocks.reshape(self.num_layers, need.size)
+            new_blocks = np.asarray(self._take(need.size * L), dtype=np.int32).reshape(L, need.size)
             self.h_tables[:, need, idx] = new_blocks
-            l_idx = torch.arange(self.num_layers, device=self.device)[:, None]
-            self.d_tables[l_idx, torch.from_numpy(need).to(self.device)[None, :],
-                          torch.from_numpy(idx).to(self.device)[None, :]] = torch.from_numpy(new_blocks).to(self.device)
-        slots = np.full((self.num_layers, self.max_seqs), -1, dtype=np.int64)
+            h_grow[0, : need.size] = need
+            h_grow[1, : need.size] = idx
+            h_blocks[:, : need.size] = new_blocks
+        h_slots[:] = -1
         blk = self.h_tables[:, act, pos // B].astype(np.int64)      # [L, n_act]
-        slots[:, act] = blk * B + pos % B
-        lens = np.zeros(self.max_seqs, dtype=np.int32)
-        lens[act] = self.h_lens[act] + (1 if attend_to_new_token else 0)
-        self._pin_slots.copy_(torch.from_numpy(slots))
-        self._pin_lens.copy_(torch.from_numpy(lens))
-        self.d_slots.copy_(self._pin_slots, non_blocking=True)
-        self.d_lens.copy_(self._pin_lens, non_blocking=True)
+        h_slots[:, act] = blk * B + pos % B
+        h_lens[:] = 0
+        h_lens[act] = self.h_lens[act] + (1 if attend_to_new_token else 0)
+        h_pos[:] = 0
+        h_pos[act] = pos
+
+        # one H2D copy, then device-side unpacking (all asynchronous on the current stream)
+        self._d_stage.copy_(buf, non_blocking=True)
+        if ev is not None:
+            ev.record()
+        self._ring[self._ring_i][2] = True
+        self._ring_i = (self._ring_i + 1) % len(self._ring)
+        ds = self._d_stage
+        self.d_slots.copy_(ds[: self._o_pos].view(torch.int64).view(L, S))
+        self.d_pos.copy_(ds[self._o_pos: self._o_grow].view(torch.int64))
+        self.d_lens.copy_(ds[self._o_lens: self._o_blocks].view(torch.int32))
+        if need.size:
+            n = int(need.size)
+            grow = ds[self._o_grow: self._o_lens].view(torch.int64).view(2, S)
+            blocks = ds[self._o_blocks:].view(torch.int32).view(L, S)
+            l_idx = torch.arange(L, device=self.device)[:, None]
+            self.d_tables[l_idx, grow[0, :n][None, :], grow[1, :n][None, :]] = blocks[:, :n]
         self.h_lens[act] += 1
 
     def positions(self) -> np.ndarray:
@@ -330,11 +371,11 @@ class GPT2Decoder:
     # -- CUDA-graph capture of the decode step -----------------------------------------------------
     def capture_decode_graph(self, kv: BatchedKVState) -> None:
         """Capture decode_forward + greedy argmax for kv.max_seqs rows into one CUDA graph.  Inputs
-        live in static buffers (`g_ids`, `g_pos`, and kv.d_slots / d_tables / d_lens, which
-        begin_decode_step updates in place); outputs in `g_logits`, `g_next`."""
+        live in static buffers (`g_ids`, and kv.d_pos / d_slots / d_tables / d_lens, which
+        begin_decode_step updates in place; `g_pos` is kv.d_pos); outputs in `g_logits`, `g_next`."""
         S = kv.max_seqs
         self.g_ids = torch.zeros(S, dtype=torch.int64, device=self.device)
-        self.g_pos = torch.zeros(S, dtype=torch.int64, device=self.device)
+        self.g_pos = kv.d_pos
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                                   # warm-up outside capture
@@ -372,14 +413,12 @@ def greedy_generate(model: GPT2Decoder, kv: BatchedKVState, prompts: Sequence[Se
     if use_graph and max_new_tokens > 1:
         model.capture_decode_graph(kv)
     for _ in range(max_new_tokens - 1):
-        kv.begin_decode_step(attend_to_new_token=True)
-        pos = torch.from_numpy(kv.positions()).to(dev, non_blocking=True)
+        kv.begin_decode_step(attend_to_new_token=True)              # publishes kv.d_pos (= model.g_pos) too
         if use_graph:
             model.g_ids.copy_(cur)
-            model.g_pos.copy_(pos)
             cur = model.replay_decode_graph().clone()
         else:
-            cur = model.greedy(model.decode_forward(cur, pos, kv))
+            cur = model.greedy(model.decode_forward(cur, kv.d_pos, kv))
         out.append(cur)
     ids = torch.stack(out, dim=1)[:n].cpu().tolist()
     return ids
