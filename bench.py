@@ -385,13 +385,12 @@ def run_full_model(args, dev, world, rank):
     assert len(owned) == LAYERS * S * nblk
     ids = torch.randint(0, shape.vocab_size, (S,), generator=g, device=dev)
     kv.begin_decode_step()
-    model.capture_decode_graph(kv)
+    model.capture_decode_graph(kv, feed_back=True)
     model.g_ids.copy_(ids)
 
     def step():
         kv.begin_decode_step()                # host bookkeeping + one pinned H2D copy, asynchronous
-        nxt = model.replay_decode_graph()
-        model.g_ids.copy_(nxt)
+        model.replay_decode_graph()           # ... the graph ends by feeding the sampled ids back
 
     for _ in range(3):
         step()

@@ -75,27 +75,35 @@ class BatchedKVState:
         self.h_lens = np.zeros(max_seqs, dtype=np.int32)
         self.active = np.zeros(max_seqs, dtype=bool)
         self.d_tables = torch.full((num_layers, max_seqs, max_blocks_per_seq), -1, dtype=torch.int32, device=device)
-        self.d_lens = torch.zeros(max_seqs, dtype=torch.int32, device=device)       # seq_lens passed to attention
-        self.d_slots = torch.full((num_layers, max_seqs), -1, dtype=torch.int64, device=device)
-        self.d_pos = torch.zeros(max_seqs, dtype=torch.int64, device=device)       # position ids of the new tokens
-        # Per-step host->device staging: ONE packed pinned buffer [slots int64 | positions int64 | new-block
-        # (seq, column) int64 pairs | lens int32 | new block ids int32] and one async copy per step.  A ring of
-        # buffers, each guarded by an event recorded after its copy, lets the host prepare step t+1 .. t+RING-1
-        # while the GPU still runs step t (nothing on the step path synchronises the host with the device).
+        # Per-step host->device staging: ONE packed buffer [slots int64 [L,S] | positions int64 [S] | flat table
+        # indices of newly appended blocks int64 [L,S] | lens int32 [S] | new block ids int32 [L,S]] and one async
+        # copy per step.  d_slots / d_pos / d_lens ARE views of the device copy (no unpacking kernels); only a
+        # step that appends blocks launches one scatter into d_tables.  On the host a ring of pinned buffers, each
+        # guarded by an event recorded after its copy, lets the host prepare steps ahead of the GPU: nothing on
+        # the step path synchronises the host with the device.
         L, S = num_layers, max_seqs
         self._o_pos = L * S * 8
         self._o_grow = self._o_pos + S * 8
-        self._o_lens = self._o_grow + 2 * S * 8
+        self._o_lens = self._o_grow + L * S * 8
         self._o_blocks = self._o_lens + S * 4
         self._stage_bytes = self._o_blocks + L * S * 4
         self._ring = []
         for _ in range(4):
-            buf = torch.empty(self._stage_bytes, dtype=torch.uint8)
+            buf = torch.zeros(self._stage_bytes, dtype=torch.uint8)
             if device.type == "cuda":
                 buf = buf.pin_memory()
             self._ring.append([buf, torch.cuda.Event() if device.type == "cuda" else None, False])
         self._ring_i = 0
-        self._d_stage = torch.empty(self._stage_bytes, dtype=torch.uint8, device=device)
+        ds = self._d_stage = torch.zeros(self._stage_bytes, dtype=torch.uint8, device=device)
+        self.d_slots = ds[: self._o_pos].view(torch.int64).view(L, S)               # slot_mapping per layer
+        self.d_slots.fill_(-1)
+        self.d_pos = ds[self._o_pos: self._o_grow].view(torch.int64)                # position ids of the new tokens
+        self._d_grow = ds[self._o_grow: self._o_lens].view(torch.int64)             # [L*S] flat indices into d_tables
+        self.d_lens = ds[self._o_lens: self._o_blocks].view(torch.int32)            # seq_lens passed to attention
+        self._d_blocks = ds[self._o_blocks:].view(torch.int32)                      # [L*S] new block ids
+        # first use of the scatter kernel pays a one-off module load: do it now, not inside a decode step
+        self.d_tables.view(-1).scatter_(0, torch.zeros(1, dtype=torch.int64, device=device),
+                                        torch.full((1,), -1, dtype=torch.int32, device=device))
 
     # -- allocation ---------------------------------------------------------------------------
     def _take(self, n: int) -> List[int]:
@@ -155,18 +163,20 @@ class BatchedKVState:
         hb = buf.numpy()
         h_slots = hb[: self._o_pos].view(np.int64).reshape(L, S)
         h_pos = hb[self._o_pos: self._o_grow].view(np.int64)
-        h_grow = hb[self._o_grow: self._o_lens].view(np.int64).reshape(2, S)
+        h_grow = hb[self._o_grow: self._o_lens].view(np.int64)
         h_lens = hb[self._o_lens: self._o_blocks].view(np.int32)
-        h_blocks = hb[self._o_blocks:].view(np.int32).reshape(L, S)
+        h_blocks = hb[self._o_blocks:].view(np.int32)
 
         need = act[pos % B == 0]                                    # last block full (or empty): append one
-        if need.size:
+        n_new = int(need.size) * L
+        if n_new:
             idx = (self.h_lens[need] // B).astype(np.int64)
-            new_blocks = np.asarray(self._take(need.size * L), dtype=np.int32).reshape(L, need.size)
+            new_blocks = np.asarray(self._take(n_new), dtype=np.int32).reshape(L, need.size)
             self.h_tables[:, need, idx] = new_blocks
-            h_grow[0, : need.size] = need
-            h_grow[1, : need.size] = idx
-            h_blocks[:, : need.size] = new_blocks
+            MB = self.max_blocks_per_seq
+            flat = (np.arange(L, dtype=np.int64)[:, None] * S + need[None, :]) * MB + idx[None, :]
+            h_grow[:n_new] = flat.reshape(-1)
+            h_blocks[:n_new] = new_blocks.reshape(-1)
         h_slots[:] = -1
         blk = self.h_tables[:, act, pos // B].astype(np.int64)      # [L, n_act]
         h_slots[:, act] = blk * B + pos % B
@@ -175,22 +185,14 @@ class BatchedKVState:
         h_pos[:] = 0
         h_pos[act] = pos
 
-        # one H2D copy, then device-side unpacking (all asynchronous on the current stream)
+        # one H2D copy publishes d_slots / d_pos / d_lens; appended blocks are scattered into d_tables
         self._d_stage.copy_(buf, non_blocking=True)
         if ev is not None:
             ev.record()
         self._ring[self._ring_i][2] = True
         self._ring_i = (self._ring_i + 1) % len(self._ring)
-        ds = self._d_stage
-        self.d_slots.copy_(ds[: self._o_pos].view(torch.int64).view(L, S))
-        self.d_pos.copy_(ds[self._o_pos: self._o_grow].view(torch.int64))
-        self.d_lens.copy_(ds[self._o_lens: self._o_blocks].view(torch.int32))
-        if need.size:
-            n = int(need.size)
-            grow = ds[self._o_grow: self._o_lens].view(torch.int64).view(2, S)
-            blocks = ds[self._o_blocks:].view(torch.int32).view(L, S)
-            l_idx = torch.arange(L, device=self.device)[:, None]
-            self.d_tables[l_idx, grow[0, :n][None, :], grow[1, :n][None, :]] = blocks[:, :n]
+        if n_new:
+            self.d_tables.view(-1).scatter_(0, self._d_grow[:n_new], self._d_blocks[:n_new])
         self.h_lens[act] += 1
 
     def positions(self) -> np.ndarray:
@@ -369,10 +371,11 @@ class GPT2Decoder:
         return torch.argmax(logits, dim=-1)
 
     # -- CUDA-graph capture of the decode step -----------------------------------------------------
-    def capture_decode_graph(self, kv: BatchedKVState) -> None:
+    def capture_decode_graph(self, kv: BatchedKVState, feed_back: bool = False) -> None:
         """Capture decode_forward + greedy argmax for kv.max_seqs rows into one CUDA graph.  Inputs
         live in static buffers (`g_ids`, and kv.d_pos / d_slots / d_tables / d_lens, which
-        begin_decode_step updates in place; `g_pos` is kv.d_pos); outputs in `g_logits`, `g_next`."""
+        begin_decode_step updates in place; `g_pos` is kv.d_pos); outputs in `g_logits`, `g_next`.
+        feed_back=True also copies `g_next` into `g_ids` at the end of the graph (free-running greedy decode)."""
         S = kv.max_seqs
         self.g_ids = torch.zeros(S, dtype=torch.int64, device=self.device)
         self.g_pos = kv.d_pos
@@ -387,6 +390,8 @@ class GPT2Decoder:
         with torch.cuda.graph(self._graph):
             self.g_logits = self.decode_forward(self.g_ids, self.g_pos, kv)
             self.g_next = self.greedy(self.g_logits)
+            if feed_back:                 # the sampled ids become the next step's input inside the graph
+                self.g_ids.copy_(self.g_next)
 
     def replay_decode_graph(self) -> torch.Tensor:
         self._graph.replay()
