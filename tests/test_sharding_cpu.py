@@ -58,6 +58,16 @@ def _worker(rank, world, port, out_dir):
         assert torch.equal(state["h.0.ln.weight"], torch.randn(16))
         assert torch.equal(state["h.0.attn.w"], torch.randn(16, 48).half())
         assert int(state["step"]) == 0
+        # the decode driver's weight broadcast also refreshes what it derived from the weights (padded lm_head)
+        from vllmini_b200.decode import GPT2Decoder, GPT2Shape, synthetic_gpt2_state_dict
+        shape = GPT2Shape(n_layer=1, n_head=2, n_embd=16, vocab_size=37, n_positions=8)
+        model = GPT2Decoder(shape, torch.device("cpu"), dtype=torch.float32)
+        model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=rank))
+        model.broadcast_weights(src=0)
+        wte_rank0 = synthetic_gpt2_state_dict(shape, seed=0)["transformer.wte.weight"]
+        assert torch.equal(model.w["transformer.wte.weight"], wte_rank0)
+        assert model._lm_head_padded.shape == (64, 16) and torch.equal(model._lm_head_padded[:37], wte_rank0)
+        assert not model._lm_head_padded[37:].any()
         # request sharding + host-side gather of results
         reqs = list(range(11))
         mine = sharding.shard_requests(reqs, world, rank)

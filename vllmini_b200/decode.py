@@ -255,13 +255,19 @@ class GPT2Decoder:
         self.w = {k: v.detach().to(device=self.device, dtype=self.dtype).contiguous() for k, v in sd.items()
                   if k != "lm_head.weight"}
         self.w["lm_head.weight"] = self.w["transformer.wte.weight"]
-        # decode-time lm_head operand: the tied embedding padded to a multiple of 64 rows.  vocab 50257 is odd, so
-        # the [S, E] x [E, V] GEMM has an unaligned leading dimension and cuBLAS falls back to a legacy kernel
-        # (182 us vs ~30 us at S=256); the zero rows only add logits that are sliced away again.
-        V, E = self.w["lm_head.weight"].shape
-        self._lm_head_padded = torch.zeros(((V + 63) // 64 * 64, E), dtype=self.dtype, device=self.device)
-        self._lm_head_padded[:V].copy_(self.w["lm_head.weight"])
+        self._lm_head_padded = None
+        self._refresh_derived()
         self._graph = None
+
+    def _refresh_derived(self) -> None:
+        """Decode-time lm_head operand: the tied embedding padded to a multiple of 64 rows.  vocab 50257 is odd, so
+        the [S, E] x [E, V] GEMM has an unaligned leading dimension and cuBLAS falls back to a legacy kernel
+        (182 us vs 23 us at S=256); the zero rows only add logits that are sliced away again.  Rebuilt in place
+        whenever the weights change (load, broadcast) so that a captured graph keeps a valid pointer."""
+        V, E = self.w["lm_head.weight"].shape
+        if self._lm_head_padded is None or self._lm_head_padded.shape != ((V + 63) // 64 * 64, E):
+            self._lm_head_padded = torch.zeros(((V + 63) // 64 * 64, E), dtype=self.dtype, device=self.device)
+        self._lm_head_padded[:V].copy_(self.w["lm_head.weight"])
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return self.w
@@ -270,6 +276,7 @@ class GPT2Decoder:
         """The path's only collective: replicate the weights from rank `src` (NCCL over NVLink)."""
         from . import sharding
         sharding.broadcast_state_dict(self.w, src=src)
+        self._refresh_derived()
 
     # -- building blocks -----------------------------------------------------------------------
     def _ln(self, x, prefix):
