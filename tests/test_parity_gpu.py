@@ -38,7 +38,10 @@ def _native_path_is_the_one_running():
 
 # ------------------------------------------------------------------------------ reshape_and_cache
 @pytest.mark.parametrize("B,H,D,T,strided", [(16, 12, 64, 3, False), (16, 12, 64, 256, True), (8, 20, 64, 77, True),
-                                             (32, 12, 64, 1000, True), (16, 4, 128, 33, False)])
+                                             (32, 12, 64, 1000, True), (16, 4, 128, 33, False),
+                                             # the other head sizes, decode-sized (warp kernel) and prefill-sized (tile)
+                                             (8, 3, 80, 40, True), (16, 3, 80, 700, True), (16, 2, 96, 513, False),
+                                             (8, 2, 112, 600, True), (32, 2, 192, 90, True), (16, 2, 256, 1030, True)])
 def test_reshape_and_cache_bit_exact(B, H, D, T, strided):
     from vllmini_b200 import ops
     rng = np.random.default_rng(T)
@@ -399,10 +402,10 @@ def test_paged_attention_v2_signature_gives_v1_result():
     assert_close_to_truth(out.cpu().numpy(), truth.astype(np.float64), what="v2")
 
 
-def test_reshape_and_cache_flash_bit_exact(ref_ext):
+@pytest.mark.parametrize("T,H,D,B,NB", [(53, 12, 64, 16, 6), (20, 3, 80, 8, 4), (300, 2, 256, 32, 10)])
+def test_reshape_and_cache_flash_bit_exact(T, H, D, B, NB, ref_ext):
     from vllmini_b200 import ops
     rng = np.random.default_rng(11)
-    T, H, D, B, NB = 53, 12, 64, 16, 6
     qkv = rng.standard_normal((T, 3 * H * D)).astype(np.float16)
     slots = rng.permutation(NB * B)[:T].astype(np.int64)
     slots[7] = -1
