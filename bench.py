@@ -251,16 +251,18 @@ class DecodeHotPath:
         torch = self.torch
         for l in range(LAYERS):
             q, k, v = self.views(self.qkv, l)
-            ops.reshape_and_cache(k, v, self.key_cache, self.value_cache, self.slots[l], "auto", 1.0)
             probe = attn_events is not None and l == probe_layer
             if probe:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                er, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                er.record()
+            ops.reshape_and_cache(k, v, self.key_cache, self.value_cache, self.slots[l], "auto", 1.0)
+            if probe:
                 e0.record()
             ops.paged_attention_v1(self.out[l], q, self.key_cache, self.value_cache, H, self.scale,
                                    self.block_tables[l], self.seq_lens, B, CTX, None, "auto", 1.0, 0, 0, 1, 1, 0)
             if probe:
                 e1.record()
-                attn_events.append((e0, e1))
+                attn_events.append((er, e0, e1))
 
 
 class HostDrivenStep:
@@ -437,9 +439,11 @@ def run_gpu_arm(args):
                            "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever
+    # a library prints (NCCL writes its version banner to stdout) cannot end up next to the result
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from vllmini_b200 import _native, ops  # raises if libvllmini_b200.so is missing
@@ -472,7 +476,8 @@ def run_gpu_arm(args):
     barrier()
     launches = _native.launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
-    attn_us = [a.elapsed_time(b) * 1e3 for a, b in attn_events]
+    attn_us = [a.elapsed_time(b) * 1e3 for _, a, b in attn_events]
+    resh_us = [r.elapsed_time(a) * 1e3 for r, a, _ in attn_events]
 
     # ---- context row: the same step with the fused append+attend launch (12 launches instead of 24) ----
     def fused_step():
@@ -592,7 +597,13 @@ def run_gpu_arm(args):
                          "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": ab, "mean_launch_us": attn_mean_us,
                          "median_launch_us": statistics.median(attn_us),
-                         "launches_timed": len(attn_us), "attention_share_of_step": attn_mean_us * LAYERS / (ms_step * 1e3),
+                         "launches_timed": len(attn_us),
+                         # the other kernel of the step, probed the same way (event-to-event, so each figure carries
+                         # its launch gap); compare the share with the ncu launch list in profiles/
+                         "reshape_and_cache_mean_launch_us": sum(resh_us) / len(resh_us),
+                         "attention_share_of_step_kernels": attn_mean_us / (attn_mean_us + sum(resh_us) / len(resh_us)),
+                         "probed_layer_us_x12_over_step": (attn_mean_us + sum(resh_us) / len(resh_us)) * LAYERS
+                                                          / (ms_step * 1e3),
                          "traffic": recorded_traffic()},
         }
         if fused_ms > 0:
@@ -613,7 +624,8 @@ def run_gpu_arm(args):
             except Exception as e:  # the GPU numbers stand even if the host leg cannot run
                 line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e!r}"}
-        print(json.dumps(line), flush=True)
+        result_out.write(json.dumps(line) + "\n")
+        result_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
