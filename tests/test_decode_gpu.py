@@ -215,3 +215,28 @@ def test_async_step_publishing_ring_never_tears():
     for step, (got, exp) in enumerate(zip(snaps, want)):
         for g_, e_ in zip(got, exp):
             assert torch.equal(g_.cpu(), e_), f"step {step}"
+
+
+def test_graphed_bucket_padded_prefill_equals_eager_prefill():
+    """prefill(graph_bucket=16) pads the prompt, replays a CUDA graph per padded length, and must produce the same
+    last-position logits and the same cache contents as the eager prefill."""
+    g, shape = _load("gpt2_greedy_tiny")
+    dev = torch.device("cuda:0")
+    model = GPT2Decoder(shape, dev)
+    model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=5))
+    rng = np.random.default_rng(8)
+
+    def fresh():
+        return BatchedKVState(shape.n_layer * 2 * 4, shape.n_layer, shape.n_head, shape.head_size, 16, 2, 4, dev)
+
+    kv_e, kv_g = fresh(), fresh()
+    for row, T in ((0, 37), (1, 45)):                    # both pad to 48: the second replay reuses the graph
+        ids = torch.tensor(rng.integers(0, shape.vocab_size, size=T), device=dev)
+        le = model.prefill(ids, kv_e, row)
+        lg = model.prefill(ids, kv_g, row, graph_bucket=16).clone()
+        assert (le.float() - lg.float()).abs().max().item() < 2e-2
+        assert int(le.argmax()) == int(lg.argmax())
+    assert len(model._prefill_graphs) == 1
+    torch.cuda.synchronize()
+    assert torch.equal(kv_e.key_cache, kv_g.key_cache) and torch.equal(kv_e.value_cache, kv_g.value_cache)
+    assert np.array_equal(kv_e.h_tables, kv_g.h_tables)

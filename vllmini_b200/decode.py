@@ -27,6 +27,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 import torch.nn.functional as F
+from torch.nn.attention import SDPBackend, sdpa_kernel
 
 from . import ops
 
@@ -118,15 +119,16 @@ class BatchedKVState:
         B = self.block_size
         nblk = (prompt_len + B - 1) // B
         pos = np.arange(prompt_len)
-        mappings = []
-        for l in range(self.num_layers):
-            blocks = np.asarray(self._take(nblk), dtype=np.int32)
-            self.h_tables[l, seq, :nblk] = blocks
-            mappings.append(torch.from_numpy(blocks[pos // B].astype(np.int64) * B + pos % B).to(self.device))
+        if len(self.free_blocks) < nblk * self.num_layers:
+            raise RuntimeError("No free blocks available")            # kv_cache.py:22-23
+        for l in range(self.num_layers):                              # layer by layer, FIFO (kv_cache.py:25-26)
+            self.h_tables[l, seq, :nblk] = np.asarray(self._take(nblk), dtype=np.int32)
+        slots = self.h_tables[:, seq, pos // B].astype(np.int64) * B + pos % B      # [L, prompt_len]
         self.h_lens[seq] = prompt_len
         self.active[seq] = True
         self.d_tables[:, seq].copy_(torch.from_numpy(self.h_tables[:, seq]), non_blocking=True)
-        return mappings
+        d_slots = torch.from_numpy(np.ascontiguousarray(slots)).to(self.device)   # one upload for all layers
+        return [d_slots[l] for l in range(self.num_layers)]
 
     def free(self, seq: int) -> None:
         """Return a sequence's blocks to the BACK of the free list (kv_cache.py:81-86)."""
@@ -232,7 +234,7 @@ def synthetic_gpt2_state_dict(shape: GPT2Shape, seed: int = 0, dtype=torch.float
 
 
 class GPT2Decoder:
-    """GPT-2 forward for serving: prefill (eager causal attention, like gpt2.py:46-59, 71-78) and
+    """GPT-2 forward for serving: prefill (causal attention over the prompt, like gpt2.py:46-59, 71-78) and
     batched single-token decode through the paged-attention hot path.
 
     Parameter names and shapes are the reference GPT2LMHeadModel's (nn.Linear [out, in] weights,
@@ -249,6 +251,7 @@ class GPT2Decoder:
         self.w: Dict[str, torch.Tensor] = {}
         self.scale = shape.head_size ** -0.5
         self._graph = None
+        self._prefill_graphs: Dict = {}
 
     # -- weights -----------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -258,6 +261,7 @@ class GPT2Decoder:
         self._lm_head_padded = None
         self._refresh_derived()
         self._graph = None
+        self._prefill_graphs = {}
 
     def _refresh_derived(self) -> None:
         """Decode-time lm_head operand: the tied embedding padded to a multiple of 64 rows.  vocab 50257 is odd, so
@@ -287,29 +291,70 @@ class GPT2Decoder:
         h = F.linear(x, self.w[p + "mlp.c_fc.weight"], self.w[p + "mlp.c_fc.bias"])
         return F.linear(F.gelu(h), self.w[p + "mlp.c_proj.weight"], self.w[p + "mlp.c_proj.bias"])
 
-    # -- prefill: one sequence, eager causal attention + reshape_and_cache -----------------------
-    @torch.no_grad()
-    def prefill(self, input_ids: torch.Tensor, kv: BatchedKVState, seq: int) -> torch.Tensor:
-        """input_ids [T] -> logits of the last position [vocab].  K/V of all T tokens are scattered
-        into the pool through the hot path's reshape_and_cache (gpt2.py:44)."""
+    # -- prefill: one sequence, causal attention over the prompt + reshape_and_cache -----------------------
+    def _prefill_forward(self, input_ids: torch.Tensor, slot_maps, kv: BatchedKVState, last: torch.Tensor):
+        """input_ids [T], slot_maps[layer] [T] (-1 = padding), `last` int64 [1] (index of the last real token)
+        -> logits of that position [vocab]."""
         s = self.shape
         T = input_ids.numel()
         H, D = s.n_head, s.head_size
-        slot_maps = kv.add_sequence(seq, T)
         x = self.w["transformer.wte.weight"][input_ids] + self.w["transformer.wpe.weight"][:T]
-        mask = torch.full((T, T), float("-inf"), device=self.device, dtype=torch.float32).triu(1)
         for i in range(s.n_layer):
             p = f"transformer.h.{i}."
             qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
             q, k, v = (t.view(T, H, D) for t in qkv.split(s.n_embd, dim=-1))      # strided views, stride 3*E
             ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, slot_maps[i], "auto", 1.0)
-            att = torch.matmul(q.transpose(0, 1).float(), k.transpose(0, 1).float().transpose(-1, -2)) * self.scale
-            att = torch.softmax(att + mask, dim=-1)
-            o = torch.matmul(att, v.transpose(0, 1).float()).transpose(0, 1).reshape(T, s.n_embd).to(self.dtype)
+            # causal attention over the prompt (gpt2.py:46-59, 71-78): a library kernel, not the paged path.  The
+            # memory-efficient backend is pinned: cuDNN's builds a plan per prompt length (45-95 ms each on B200).
+            with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):
+                o = F.scaled_dot_product_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None],
+                                                   v.transpose(0, 1)[None], is_causal=True, scale=self.scale)[0]
+            o = o.transpose(0, 1).reshape(T, s.n_embd)
             x = x + F.linear(o, self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
             x = x + self._mlp(self._ln(x, p + "ln_2"), p)
-        x = self._ln(x[-1:], "transformer.ln_f")
+        x = self._ln(x.index_select(0, last), "transformer.ln_f")
         return F.linear(x, self.w["lm_head.weight"])[0]
+
+    @torch.no_grad()
+    def prefill(self, input_ids: torch.Tensor, kv: BatchedKVState, seq: int, graph_bucket: int = 0) -> torch.Tensor:
+        """input_ids [T] -> logits of the last position [vocab].  K/V of all T tokens are scattered
+        into the pool through the hot path's reshape_and_cache (gpt2.py:44).
+
+        graph_bucket > 0: the prompt is padded to a multiple of `graph_bucket` tokens (padding carries slot -1, is
+        never attended by real tokens under the causal mask and is never stored) and the forward pass is replayed
+        from a CUDA graph captured once per padded length -- prefill is ~200 small launches, i.e. host-bound when
+        issued eagerly.  The returned tensor is then a static buffer, valid until the next graphed prefill."""
+        T = input_ids.numel()
+        slot_maps = kv.add_sequence(seq, T)
+        if graph_bucket <= 0 or self.device.type != "cuda":
+            last = torch.full((1,), T - 1, dtype=torch.int64, device=self.device)
+            return self._prefill_forward(input_ids, slot_maps, kv, last)
+        Tb = min((T + graph_bucket - 1) // graph_bucket * graph_bucket, self.shape.n_positions)
+        key = (Tb, id(kv))
+        st = self._prefill_graphs.get(key)
+        if st is None:
+            L = self.shape.n_layer
+            st = {"ids": torch.zeros(Tb, dtype=torch.int64, device=self.device),
+                  "slots": torch.full((L, Tb), -1, dtype=torch.int64, device=self.device),
+                  "last": torch.zeros(1, dtype=torch.int64, device=self.device)}
+            rows = [st["slots"][l] for l in range(L)]
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                              # warm-up outside capture (all slots -1)
+                self._prefill_forward(st["ids"], rows, kv, st["last"])
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            st["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st["graph"]):
+                st["logits"] = self._prefill_forward(st["ids"], rows, kv, st["last"])
+            self._prefill_graphs[key] = st
+        st["ids"].zero_()
+        st["ids"][:T].copy_(input_ids)
+        st["slots"].fill_(-1)
+        st["slots"][:, :T].copy_(torch.stack(slot_maps))
+        st["last"].fill_(T - 1)
+        st["graph"].replay()
+        return st["logits"]
 
     # -- decode: all sequences, one token each ----------------------------------------------------
     @torch.no_grad()

@@ -35,7 +35,7 @@ from .decode import BatchedKVState
 class BatchedScheduler:
     def __init__(self, model, kv: BatchedKVState, max_length: int, eos_token_id: Optional[int] = None,
                  sampling: str = "greedy", top_k: int = 50, temperature: float = 1.0, seed: int = 0,
-                 use_graph: bool = False, reference_off_by_one: bool = False):
+                 use_graph: bool = False, reference_off_by_one: bool = False, prefill_bucket: int = 128):
         if sampling not in ("greedy", "top_k"):
             raise ValueError("sampling must be 'greedy' or 'top_k'")
         self.model, self.kv = model, kv
@@ -44,6 +44,7 @@ class BatchedScheduler:
         self.eos_token_id = eos_token_id
         self.sampling, self.top_k, self.temperature = sampling, int(top_k), float(temperature)
         self.use_graph = use_graph
+        self.prefill_bucket = int(prefill_bucket) if use_graph else 0     # graphed prefill, padded to this multiple
         self.attend_to_new_token = not reference_off_by_one
         self.device = kv.device
         S = kv.max_seqs
@@ -104,7 +105,11 @@ class BatchedScheduler:
             self.pending.popleft()
             self.rows[row] = seq_id
             self.row_of[seq_id] = row
-            logits = self.model.prefill(torch.tensor(ids, dtype=torch.int64, device=self.device), kv, row)
+            t_ids = torch.tensor(ids, dtype=torch.int64, device=self.device)
+            if self.prefill_bucket:
+                logits = self.model.prefill(t_ids, kv, row, graph_bucket=self.prefill_bucket)
+            else:
+                logits = self.model.prefill(t_ids, kv, row)
             if self._logits is None:
                 self._logits = torch.zeros((kv.max_seqs, logits.shape[-1]), dtype=logits.dtype, device=self.device)
             self._logits[row].copy_(logits)
