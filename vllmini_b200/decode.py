@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import collections
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -332,9 +333,12 @@ class GPT2Decoder:
         Tb = min((T + graph_bucket - 1) // graph_bucket * graph_bucket, self.shape.n_positions)
         key = (Tb, id(kv))
         st = self._prefill_graphs.get(key)
+        if st is not None and st["kv"]() is not kv:      # the id was recycled by a different (newer) pool
+            st = None
         if st is None:
             L = self.shape.n_layer
-            st = {"ids": torch.zeros(Tb, dtype=torch.int64, device=self.device),
+            st = {"kv": weakref.ref(kv),
+                  "ids": torch.zeros(Tb, dtype=torch.int64, device=self.device),
                   "slots": torch.full((L, Tb), -1, dtype=torch.int64, device=self.device),
                   "last": torch.zeros(1, dtype=torch.int64, device=self.device)}
             rows = [st["slots"][l] for l in range(L)]
