@@ -124,3 +124,19 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _native.load()
+
+
+def test_header_is_plain_c_and_abi_validates_arguments_from_a_c_program(tmp_path):
+    """tests/c/abi_smoke.c includes include/vllmini_b200.h as C (gcc -std=c99 -pedantic), links the library and
+    exercises every argument-validation path that needs no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-L", libdir, "-lvllmini_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi_smoke: ok" in out.stdout, out.stdout + out.stderr
