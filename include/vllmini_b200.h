@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 2
+#define VB200_ABI_VERSION 1
 
 enum {
   VB200_OK = 0,
@@ -87,15 +87,11 @@ int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_c
  * head_size]: one new token per sequence (decode), row strides key_stride / value_stride.  The token of
  * sequence s must sit at position >= seq_lens[s] - 1 of that sequence (seq_lens[s] - 1 if it attends to
  * itself; seq_lens[s] with the reference scheduler's convention).  slot_mapping[s] < 0 skips the write.
- * seq_order (may be NULL): a permutation of 0..num_seqs-1 giving the order in which sequences are handed to the
- * CTA dispatcher; a caller that knows the lengths passes them longest first so that the long sequences of a
- * ragged batch do not start last (results do not depend on it).
  */
 int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
                                         void* key_cache, void* value_cache, const int64_t* slot_mapping,
-                                        const int32_t* block_tables, const int32_t* seq_lens,
-                                        const int32_t* seq_order, int32_t num_seqs, int32_t num_heads,
-                                        int32_t num_kv_heads, int32_t head_size,
+                                        const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
+                                        int32_t num_heads, int32_t num_kv_heads, int32_t head_size,
                                         int32_t block_size, int32_t max_num_blocks_per_seq, int32_t max_seq_len,
                                         int64_t q_stride, int64_t key_stride, int64_t value_stride,
                                         int64_t kv_block_stride, int64_t kv_head_stride, float scale,

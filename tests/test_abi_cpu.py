@@ -35,7 +35,7 @@ def test_library_exports_every_header_symbol():
 
 def test_abi_version_and_counters():
     lib = _native.load()
-    assert lib.vb200_abi_version() == _native.ABI_VERSION == 2
+    assert lib.vb200_abi_version() == _native.ABI_VERSION == 1
     assert _native.launch_count() >= 0
     prev = _native.set_tuning(0, 0)
     assert isinstance(prev, int)

@@ -36,7 +36,6 @@ def test_decode_step_slots_block_append_and_lens():
     assert kv.d_lens.tolist() == [4, 0, 5, 0]
     assert kv.positions().tolist() == [3, 0, 4, 0]
     assert kv.d_pos.tolist() == [3, 0, 4, 0]                  # device copy of the position ids (graph input)
-    assert kv.d_order.tolist() == [2, 0, 1, 3]                # longest context first, inactive rows last (stable)
     assert torch.equal(kv.d_tables, torch.from_numpy(kv.h_tables))
     # the reference scheduler's off-by-one (scheduler.py:96-101): seq_lens excludes the new token
     kv.begin_decode_step(attend_to_new_token=False)

@@ -522,48 +522,6 @@ def test_fused_append_equals_reshape_then_attention(self_attend, shape):
     assert_close_to_truth(out_b.cpu().numpy(), truth, what="fused append")
 
 
-def test_fused_append_dispatch_order_does_not_change_results():
-    """seq_order only permutes which CTA handles which sequence: outputs and caches are bit-identical for the
-    identity, a longest-first and a random permutation (ragged batch, split-KV off and on)."""
-    from vllmini_b200 import _native, ops
-    rng = np.random.default_rng(31)
-    S, H, D, B = 23, 12, 64, 16
-    hist = rng.integers(0, 400, size=S)
-    lens_after = hist + 1
-    q, kc, vc, bt, _ = po.make_case(S, H, D, B, lens_after, seed=5, max_blocks_per_seq=int(lens_after.max() // B + 2))
-    dev = torch.device("cuda:0")
-    k_new = torch.from_numpy(rng.standard_normal((S, H, D)).astype(np.float16)).to(dev)
-    v_new = torch.from_numpy(rng.standard_normal((S, H, D)).astype(np.float16)).to(dev)
-    slots = torch.from_numpy(bt[np.arange(S), hist // B].astype(np.int64) * B + hist % B).to(dev)
-    seq_lens = torch.from_numpy(lens_after.astype(np.int32)).to(dev)
-    bt_t, q_t = torch.from_numpy(bt).to(dev), torch.from_numpy(q).to(dev)
-    msl = int(bt.shape[1]) * B
-    orders = [None, torch.from_numpy(np.argsort(-lens_after, kind="stable").astype(np.int32)).to(dev),
-              torch.from_numpy(rng.permutation(S).astype(np.int32)).to(dev)]
-    for force_splits in (0, 3):
-        results = []
-        _native.set_tuning(force_splits, 0)
-        try:
-            for order in orders:
-                kc_t, vc_t = torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev)
-                out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
-                ops.paged_attention_v1_append(out, q_t, k_new, v_new, kc_t, vc_t, slots, H, 0.125, bt_t, seq_lens, B,
-                                              msl, seq_order=order)
-                torch.cuda.synchronize()
-                results.append((out, kc_t, vc_t))
-        finally:
-            _native.set_tuning(0, 0)
-        for out, kc_t, vc_t in results[1:]:
-            assert torch.equal(kc_t, results[0][1]) and torch.equal(vc_t, results[0][2])
-            if force_splits == 0:
-                assert torch.equal(out, results[0][0])
-            else:   # the order in which split partials arrive may differ: same merge formula, fp32 rounding only
-                assert (out.float() - results[0][0].float()).abs().max().item() < 1e-3
-    with pytest.raises(RuntimeError):
-        ops.paged_attention_v1_append(out, q_t, k_new, v_new, kc_t, vc_t, slots, H, 0.125, bt_t, seq_lens, B, msl,
-                                      seq_order=orders[1].long())
-
-
 # ------------------------------------------------------------------------------ randomized shapes
 def test_randomized_shapes_against_c_oracle():
     """60 seeded random problems: batch 1..40, heads (MHA and GQA), every head size, block 8/16/32, ragged

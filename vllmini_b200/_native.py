@@ -12,14 +12,14 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvllmini_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 1
 
 # name -> (restype, argtypes); mirrors include/vllmini_b200.h one to one
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 SYMBOLS = {
     "vb200_paged_attention_v1_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                             _i64, _i64, _i64, _f32, _vp, _sz, _i32, _vp]),
-    "vb200_paged_attention_v1_append_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+    "vb200_paged_attention_v1_append_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                                    _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _sz,
                                                    _i32, _vp]),
     "vb200_paged_attention_v1_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),

@@ -56,7 +56,6 @@ struct PaParams {
   const __half* __restrict__ new_k;
   const __half* __restrict__ new_v;
   const int64_t* __restrict__ slot_mapping;
-  const int32_t* __restrict__ seq_order;   // optional dispatch order of the sequences (longest first), or nullptr
   int64_t new_k_stride;
   int64_t new_v_stride;
   __half* kc_w;
@@ -370,6 +369,7 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   __shared__ int s_last;
 
   const int head = blockIdx.x;
+  const int seq = blockIdx.y;
   const int split = blockIdx.z;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -389,8 +389,6 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   }
   griddep_wait();
 
-  // CTAs are dispatched in blockIdx order: with a caller-supplied order the long sequences of a ragged batch go first
-  const int seq = (APPEND && p.seq_order != nullptr) ? p.seq_order[blockIdx.y] : (int)blockIdx.y;
   const UnitRange r = unit_range<B>(p, seq, split);
   if (r.empty_split) return;
   const int nstages = r.nstages, nblk = r.nblk;
@@ -939,7 +937,6 @@ struct AppendArgs {
   const void* new_k = nullptr;
   const void* new_v = nullptr;
   const int64_t* slot_mapping = nullptr;
-  const int32_t* seq_order = nullptr;
   int64_t new_k_stride = 0, new_v_stride = 0;
 };
 }  // namespace
@@ -1006,7 +1003,6 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.new_k = static_cast<const __half*>(a.new_k);
   p.new_v = static_cast<const __half*>(a.new_v);
   p.slot_mapping = a.slot_mapping;
-  p.seq_order = a.seq_order;
   p.new_k_stride = a.new_k_stride;
   p.new_v_stride = a.new_v_stride;
   p.kc_w = static_cast<__half*>(const_cast<void*>(key_cache));
@@ -1050,8 +1046,8 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
 extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
                                                    void* key_cache, void* value_cache, const int64_t* slot_mapping,
                                                    const int32_t* block_tables, const int32_t* seq_lens,
-                                                   const int32_t* seq_order, int32_t num_seqs, int32_t num_heads,
-                                                   int32_t num_kv_heads, int32_t head_size, int32_t block_size,
+                                                   int32_t num_seqs, int32_t num_heads, int32_t num_kv_heads,
+                                                   int32_t head_size, int32_t block_size,
                                                    int32_t max_num_blocks_per_seq, int32_t max_seq_len,
                                                    int64_t q_stride, int64_t key_stride, int64_t value_stride,
                                                    int64_t kv_block_stride, int64_t kv_head_stride, float scale,
@@ -1065,7 +1061,6 @@ extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query,
   a.new_k = key;
   a.new_v = value;
   a.slot_mapping = slot_mapping;
-  a.seq_order = seq_order;
   a.new_k_stride = key_stride;
   a.new_v_stride = value_stride;
   return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,

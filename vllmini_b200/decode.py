@@ -88,8 +88,7 @@ class BatchedKVState:
         self._o_grow = self._o_pos + S * 8
         self._o_lens = self._o_grow + L * S * 8
         self._o_blocks = self._o_lens + S * 4
-        self._o_order = self._o_blocks + L * S * 4
-        self._stage_bytes = self._o_order + S * 4
+        self._stage_bytes = self._o_blocks + L * S * 4
         self._ring = []
         for _ in range(4):
             buf = torch.zeros(self._stage_bytes, dtype=torch.uint8)
@@ -103,9 +102,7 @@ class BatchedKVState:
         self.d_pos = ds[self._o_pos: self._o_grow].view(torch.int64)                # position ids of the new tokens
         self._d_grow = ds[self._o_grow: self._o_lens].view(torch.int64)             # [L*S] flat indices into d_tables
         self.d_lens = ds[self._o_lens: self._o_blocks].view(torch.int32)            # seq_lens passed to attention
-        self._d_blocks = ds[self._o_blocks: self._o_order].view(torch.int32)        # [L*S] new block ids
-        self.d_order = ds[self._o_order:].view(torch.int32)                         # rows, longest context first
-        self.d_order.copy_(torch.arange(S, dtype=torch.int32))
+        self._d_blocks = ds[self._o_blocks:].view(torch.int32)                      # [L*S] new block ids
         # first use of the scatter kernel pays a one-off module load: do it now, not inside a decode step
         self.d_tables.view(-1).scatter_(0, torch.zeros(1, dtype=torch.int64, device=device),
                                         torch.full((1,), -1, dtype=torch.int32, device=device))
@@ -171,8 +168,7 @@ class BatchedKVState:
         h_pos = hb[self._o_pos: self._o_grow].view(np.int64)
         h_grow = hb[self._o_grow: self._o_lens].view(np.int64)
         h_lens = hb[self._o_lens: self._o_blocks].view(np.int32)
-        h_blocks = hb[self._o_blocks: self._o_order].view(np.int32)
-        h_order = hb[self._o_order:].view(np.int32)
+        h_blocks = hb[self._o_blocks:].view(np.int32)
 
         need = act[pos % B == 0]                                    # last block full (or empty): append one
         n_new = int(need.size) * L
@@ -191,9 +187,6 @@ class BatchedKVState:
         h_lens[act] = self.h_lens[act] + (1 if attend_to_new_token else 0)
         h_pos[:] = 0
         h_pos[act] = pos
-        # dispatch order for the attention launch: longest context first (inactive rows, length 0, last), so that the
-        # long sequences of a ragged batch are not the ones that start last; identity when all lengths are equal
-        h_order[:] = np.argsort(-h_lens.astype(np.int64), kind="stable")
 
         # one H2D copy publishes d_slots / d_pos / d_lens; appended blocks are scattered into d_tables
         self._d_stage.copy_(buf, non_blocking=True)
@@ -396,8 +389,7 @@ class GPT2Decoder:
         o = torch.empty((S, H, D), dtype=self.dtype, device=self.device)
         if self.fused_append:
             ops.paged_attention_v1_append(o, q, k, v, kv.key_cache, kv.value_cache, kv.d_slots[layer], H, self.scale,
-                                          kv.d_tables[layer], kv.d_lens, B, max_seq_len,
-                                          seq_order=getattr(kv, "d_order", None))
+                                          kv.d_tables[layer], kv.d_lens, B, max_seq_len)
         else:
             ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, kv.d_slots[layer], "auto", 1.0)
             ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale, kv.d_tables[layer], kv.d_lens,

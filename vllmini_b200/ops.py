@@ -178,14 +178,11 @@ def paged_attention_v1_append(
     seq_lens: torch.Tensor,
     block_size: int,
     max_seq_len: int,
-    seq_order: Optional[torch.Tensor] = None,
 ) -> None:
     """Extension (no reference counterpart): one launch that does exactly
     `reshape_and_cache(key, value, key_cache, value_cache, slot_mapping, "auto", 1.0)` followed by
     `paged_attention_v1(out, query, ...)` for a decode step -- key/value [num_seqs, num_kv_heads, head_size]
-    hold ONE new token per sequence, located at position >= seq_lens[s] - 1 of its sequence.  `seq_order`
-    (optional int32 permutation of the sequence indices, e.g. longest first) only changes the order in which the
-    sequences are dispatched, never the result."""
+    hold ONE new token per sequence, located at position >= seq_lens[s] - 1 of its sequence."""
     for t, name in ((out, "out"), (query, "query"), (key, "key"), (value, "value"), (key_cache, "key_cache"),
                     (value_cache, "value_cache"), (slot_mapping, "slot_mapping"), (block_tables, "block_tables"),
                     (seq_lens, "seq_lens")):
@@ -203,10 +200,6 @@ def paged_attention_v1_append(
     if not (out.is_contiguous() and block_tables.is_contiguous() and seq_lens.is_contiguous()
             and slot_mapping.is_contiguous() and key_cache.is_contiguous() and value_cache.is_contiguous()):
         raise RuntimeError("vllmini_b200: out, block_tables, seq_lens, slot_mapping and the caches must be contiguous")
-    if seq_order is not None:
-        _require_cuda(seq_order, "seq_order")
-        if seq_order.dtype is not torch.int32 or not seq_order.is_contiguous() or seq_order.numel() != num_seqs:
-            raise RuntimeError("vllmini_b200: seq_order must be a contiguous int32 tensor of num_seqs entries")
     dev = query.device
     dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     lib = _native.load()
@@ -216,7 +209,7 @@ def paged_attention_v1_append(
     rc = lib.vb200_paged_attention_v1_append_f16(
         out.data_ptr(), query.data_ptr(), key.data_ptr(), value.data_ptr(), key_cache.data_ptr(),
         value_cache.data_ptr(), slot_mapping.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
-        seq_order.data_ptr() if seq_order is not None else None, num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size),
+        num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size),
         block_tables.size(1) if block_tables.dim() == 2 else 0, int(max_seq_len),
         query.stride(0), key.stride(0), value.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
         ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, dev_index,
