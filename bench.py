@@ -352,7 +352,6 @@ def run_full_model(args, dev, world, rank):
     and argmax via the library) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
     driver of SURVEY.md 8f rank 1), CUDA-graph replayed.  Reported as context next to the hot-path
     `value`; at N>1 rank 0's weights are broadcast over NCCL first (the path's only collective)."""
-    import numpy as np
     import torch
     from vllmini_b200 import sharding
     from vllmini_b200.decode import BatchedKVState, GPT2Decoder, GPT2Shape, synthetic_gpt2_state_dict

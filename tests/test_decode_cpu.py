@@ -1,5 +1,4 @@
 """CPU tests of the batched decode driver's host logic (block bookkeeping), device='cpu'."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,5 @@
 """Property tests (hypothesis) of the batched driver's host logic on CPU: block accounting of BatchedKVState under
 random add / step / free interleavings, and the scheduler's per-request results under random workloads."""
-import numpy as np
 import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st

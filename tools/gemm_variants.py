@@ -3,7 +3,6 @@
 entry points (graph replay over 12 distinct weight sets, us per GEMM)."""
 import json
 import os
-import sys
 
 import torch
 import torch.nn.functional as F

@@ -23,7 +23,7 @@ import collections
 import math
 import weakref
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 import torch

@@ -26,7 +26,6 @@ import itertools
 import time
 from typing import Deque, Dict, List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 
 from .decode import BatchedKVState
