@@ -38,6 +38,9 @@ CONFIGS = {
     "D256": (256, 4, 256, 16, 1024),
     "D80_b8": (256, 8, 80, 8, 1024),
     "D256_b32": (256, 4, 256, 32, 1024),
+    "GQA4_d128": (256, 8, 128, 16, 1024, 32),   # 32 query heads over 8 kv heads (6th entry = query heads)
+    "GQA8_d128": (256, 4, 128, 16, 1024, 32),
+    "GQA4_d64": (256, 3, 64, 16, 1024, 12),
     "S1_8k": (1, 12, 64, 16, 8192),
     "S1_48": (1, 12, 64, 16, 48),        # vllmini's own serving shape: 1 sequence, <= 64 tokens (server.py:37-50)
     "S4_64": (4, 12, 64, 16, 64),
@@ -59,7 +62,7 @@ def algorithmic_bytes(S, H, D, B, lens):
 POOL_MULT = 1   # --pool-mult: KV pool this many times larger than the batch needs (block ids spread over it)
 
 
-def make(S, H, D, B, ctx, seed, dev, mixed=False):
+def make(S, H, D, B, ctx, seed, dev, mixed=False, QH=None):
     g = torch.Generator(device=dev).manual_seed(seed)
     if mixed:
         lens = torch.randint(128, 2049, (S,), generator=g, device=dev, dtype=torch.int32)
@@ -69,19 +72,20 @@ def make(S, H, D, B, ctx, seed, dev, mixed=False):
     NB = S * nblk * POOL_MULT
     kc = torch.empty(NB, H, D // 8, B, 8, device=dev, dtype=torch.float16).normal_(generator=g)
     vc = torch.empty(NB, H, D, B, device=dev, dtype=torch.float16).normal_(generator=g)
-    q = torch.randn(S, H, D, generator=g, device=dev, dtype=torch.float16)
+    q = torch.randn(S, QH or H, D, generator=g, device=dev, dtype=torch.float16)
     bt = torch.randperm(NB, generator=g, device=dev)[: S * nblk].to(torch.int32).view(S, nblk).contiguous()
     return q, kc, vc, bt, lens
 
 
 def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
-    S, H, D, B, ctx = CONFIGS[name]
+    S, H, D, B, ctx = CONFIGS[name][:5]
+    QH = CONFIGS[name][5] if len(CONFIGS[name]) > 5 else None
     mixed = ctx < 0
     ctx = abs(ctx)
     dev = torch.device("cuda:0")
     bytes_one = 2 * S * ctx * H * D * 2
     npools = max(2, min(6, int((1 << 30) // max(bytes_one, 1)) + 1)) if bytes_one < (1 << 30) else 2
-    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(npools)]
+    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed, QH=QH) for s in range(npools)]
     outs = [torch.empty_like(p[0]) for p in pools]
     _native.set_tuning(splits, variant)
     def call(i):
