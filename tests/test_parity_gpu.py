@@ -656,3 +656,38 @@ def test_baseline_configs_full_size_vs_reference_kernel(name, S, H, D, B, ctx, r
     err_new = np.abs(new[rows].cpu().numpy().astype(np.float64) - truth).max()
     err_ref = np.abs(ref[rows].cpu().numpy().astype(np.float64) - truth).max()
     assert err_new <= max(5e-4, err_ref), f"{name}: new {err_new:.2e} vs reference kernel {err_ref:.2e} from fp64 truth"
+
+
+# ------------------------------------------------------------------------------ grouped-query kernel
+@pytest.mark.parametrize("D,B,KVH,ratio", [(64, 16, 3, 4), (64, 8, 2, 2), (64, 32, 1, 8), (128, 16, 2, 4), (128, 32, 2, 4),
+                                           (128, 8, 1, 6), (64, 16, 2, 3)])
+def test_grouped_query_kernel_is_bit_identical_to_the_per_head_grid(D, B, KVH, ratio):
+    """num_kv_heads < num_heads takes the kernel that applies each landed tile to 4 (or 2) query heads of its kv
+    head; per head it performs the same operations in the same order as the per-query-head grid (tuning variant 8
+    forces that one), so outputs must match bit for bit -- and the fp64 oracle within tolerance.  Ratio 3 has no
+    grouped instantiation and runs the per-head grid either way."""
+    from vllmini_b200 import _native, ops
+    rng = np.random.default_rng(D + B + KVH + ratio)
+    H, S = KVH * ratio, 9
+    lens = rng.integers(0, 300, size=S).astype(np.int32)
+    lens[0], lens[1] = 1, 257
+    q, kc, vc, bt, sl = po.make_case(S, KVH, D, B, lens, seed=ratio, max_blocks_per_seq=int(lens.max() // B + 2))
+    q = rng.standard_normal((S, H, D)).astype(np.float16)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (q, kc, vc, bt, sl)]
+    outs = []
+    for variant, splits in ((0, 0), (8, 0), (0, 3), (8, 3)):
+        _native.set_tuning(splits, variant)
+        try:
+            out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+            ops.paged_attention_v1(out, t[0], t[1], t[2], KVH, 0.11, t[3], t[4], B, int(bt.shape[1]) * B, None, "auto",
+                                   1.0, 0, 0, 1, 1, 0)
+            torch.cuda.synchronize()
+            outs.append(out)
+        finally:
+            _native.set_tuning(0, 0)
+    assert torch.equal(outs[0], outs[1]), "grouped-query kernel differs from the per-head grid"
+    assert (outs[2].float() - outs[3].float()).abs().max().item() < 1e-3          # split partials: arrival order
+    truth = c_oracle().paged_attention_v1(q, kc, vc, 0.11, bt, sl, num_kv_heads=KVH, mode="exact").astype(np.float64)
+    assert_close_to_truth(outs[0].cpu().numpy(), truth, atol=1.5e-3, what="grouped-query kernel")
+    assert_close_to_truth(outs[2].cpu().numpy(), truth, atol=1.5e-3, what="grouped-query kernel, split-KV")

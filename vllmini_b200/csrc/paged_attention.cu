@@ -546,6 +546,262 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped-query variant: one CTA per (G query heads of one kv head, seq, split)
+// ---------------------------------------------------------------------------------------------
+// With num_kv_heads < num_heads the classic grid gives every QUERY head its own CTA, so a kv head's tiles are
+// fetched once per query head (the repeats hit L2, but L2 -> SM bandwidth then bounds the kernel:
+// profiles/r01k_sweep_gqa.json).  Here a landed K/V tile is applied to G query heads of its kv head before the
+// ring slot is refilled: HBM and L2 traffic per query head drop by G.  The query rows live in shared memory
+// (read per chunk, broadcast); softmax state and accumulators are per query head.  Not reached by vllmini (MHA).
+template <int D, int B, int W, int NST, int G>
+struct PaCfgG : PaCfg<D, B, W, NST> {
+  using Base = PaCfg<D, B, W, NST>;
+  static constexpr int PBUF_OFF = Base::RING;                                     // W * G * 32 halves
+  static constexpr int BAR_OFF = PBUF_OFF + W * G * 64;                           // W * NST mbarriers
+  static constexpr int RED_OFF = BAR_OFF + W * NST * 8;                           // G * W * (D + 2) floats
+  static constexpr int Q_OFF = (RED_OFF + G * W * (D + 2) * 4 + 15) / 16 * 16;    // G * D halves
+  static constexpr int SMEM = Q_OFF + G * D * 2;
+  static constexpr bool FITS = SMEM <= 227 * 1024;
+  static constexpr int kG = G;
+};
+
+template <class C>
+__device__ __forceinline__ void process_stage_gqa(uint32_t sbase, uint32_t pbuf, int lane, uint32_t qs,
+                                                  float (&m)[C::kG], float (&lsum)[C::kG],
+                                                  float (&acc)[C::kG][C::NJ], int stage_tok0, int tok_end,
+                                                  float scale_log2e) {
+  constexpr int B = C::kB, G = C::kG;
+  // ---- QK^T: every K chunk is read once and multiplied with the G query rows ----
+  float s[G];
+  {
+    float part[G][C::BPS];
+#pragma unroll
+    for (int b = 0; b < C::BPS; ++b) {
+      float c0[G], c1[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) c0[g] = c1[g] = 0.f;
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) {
+        if (chunk_ok<C>(lane, j)) {
+          const uint4 kv = lds128(sbase + b * C::TILE + (lane + 32 * j) * 16);
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            dot8(lds128(qs + (g * (C::kD / 8) + (lane + 32 * j) / B) * 16), kv, c0[g], c1[g]);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) part[g][b] = c0[g] + c1[g];
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {  // transpose-reduce as in process_stage
+      if constexpr (C::BPS == 1) {
+        s[g] = part[g][0];
+      } else if constexpr (C::BPS == 2) {
+        const bool up = lane & 16;
+        const float give = up ? part[g][0] : part[g][1];
+        s[g] = (up ? part[g][1] : part[g][0]) + __shfl_xor_sync(0xffffffffu, give, 16);
+      } else {
+        const bool up = lane & 16;
+        const float g0 = up ? part[g][0] : part[g][2];
+        const float g1 = up ? part[g][1] : part[g][3];
+        const float k0 = (up ? part[g][2] : part[g][0]) + __shfl_xor_sync(0xffffffffu, g0, 16);
+        const float k1 = (up ? part[g][3] : part[g][1]) + __shfl_xor_sync(0xffffffffu, g1, 16);
+        const bool up2 = lane & 8;
+        const float give = up2 ? k0 : k1;
+        s[g] = (up2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+    }
+  }
+  const bool tail = stage_tok0 + 32 > tok_end;  // warp-uniform
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float sg = s[g] * scale_log2e;
+    if (stage_tok0 + lane >= tok_end) sg = -INFINITY;
+    const float smax = warp_max_f32(sg);
+    if (smax > m[g]) {
+      const float alpha = ex2(m[g] - smax);
+      m[g] = smax;
+      lsum[g] *= alpha;
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) acc[g][j] *= alpha;
+    }
+    const __half p16 = __float2half_rn(ex2(sg - m[g]));
+    lsum[g] += __half2float(p16);
+    sts16(pbuf + g * 64 + lane * 2, __half_as_ushort(p16));
+  }
+  __syncwarp();
+
+  // ---- PV: every V chunk is read once and multiplied with the G probability rows ----
+#pragma unroll
+  for (int b = 0; b < C::BPS; ++b) {
+    uint4 pv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) pv[g] = lds128(pbuf + g * 64 + (b * B + (lane % C::TPR) * 8) * 2);
+    const int nv = tok_end - (stage_tok0 + b * B + (lane % C::TPR) * 8);
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) {
+      if (chunk_ok<C>(lane, j)) {
+        uint4 vv = lds128(sbase + (C::BPS + b) * C::TILE + (lane + 32 * j) * 16);
+        if (tail) vv = keep_first(vv, nv);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float c1 = 0.f;
+          dot8(pv[g], vv, acc[g][j], c1);
+          acc[g][j] += c1;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int D, int B, int W, int NST, bool APPEND, int G>
+__global__ void __launch_bounds__(W * 32) pa_v1_gqa_kernel(const PaParams p) {
+  using C = PaCfgG<D, B, W, NST, G>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int s_last;
+
+  const int head0 = blockIdx.x * G;  // first of this CTA's G query heads (all of one kv head)
+  const int seq = blockIdx.y;
+  const int split = blockIdx.z;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + C::BAR_OFF) + i * 8, 1);
+    fence_mbar_init();
+  }
+  griddep_wait();
+
+  const UnitRange r = unit_range<B>(p, seq, split);
+  if (r.empty_split) return;
+  const int nstages = r.nstages, nblk = r.nblk;
+
+  const int kv_head = head0 / (p.num_heads / p.num_kv_heads);
+  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + r.tok_begin / B;
+  const __half* kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
+  const __half* vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
+
+  const uint32_t ring = smem_u32(smem) + warp * (NST * C::STAGE);
+  const uint32_t pbuf = smem_u32(smem + C::PBUF_OFF) + warp * (G * 64);
+  const uint32_t bars = smem_u32(smem + C::BAR_OFF) + warp * (NST * 8);
+  const uint32_t qs = smem_u32(smem + C::Q_OFF);
+
+  // the G query rows -> shared memory (consecutive heads: one contiguous G*D run of the query row)
+  {
+    const __half* qrow = p.q + (int64_t)seq * p.q_stride + (int64_t)head0 * D;
+    for (int c = threadIdx.x; c < G * D / 8; c += W * 32)
+      *reinterpret_cast<uint4*>(smem + C::Q_OFF + c * 16) = ldg128(qrow + 8 * c);
+  }
+
+  // fused append: as in pa_v1_kernel, but a kv head's row is now written by exactly one CTA when G covers the group
+  const int row_warp = nstages > 0 ? (nstages - 1) % W : 0;
+  const bool row_owner = APPEND && p.new_k != nullptr && split == r.nsplit_seq - 1 && warp == row_warp;
+  int64_t new_slot = -1;
+  int64_t phys_last = -1;
+  uint4 patch_k = make_uint4(0, 0, 0, 0);
+  uint32_t patch_v[(D + 63) / 64];
+#pragma unroll
+  for (int u = 0; u < (D + 63) / 64; ++u) patch_v[u] = 0;
+  if (row_owner) {
+    new_slot = p.slot_mapping[seq];
+    const __half* ksrc = p.new_k + (int64_t)seq * p.new_k_stride + (int64_t)kv_head * D;
+    const __half* vsrc = p.new_v + (int64_t)seq * p.new_v_stride + (int64_t)kv_head * D;
+    if (lane < D / 8) patch_k = ldg128(ksrc + lane * 8);
+#pragma unroll
+    for (int u = 0; u < (D + 63) / 64; ++u)
+      if (lane + 32 * u < D / 2) patch_v[u] = __ldg(reinterpret_cast<const uint32_t*>(vsrc) + lane + 32 * u);
+    if (nstages > 0) phys_last = __ldg(table + (r.tok_end - 1 - r.tok_begin) / B);
+  }
+  __syncthreads();
+
+  auto issue_stage = [&](int st, int slot, int phys) {
+    const int blk0 = st * C::BPS;
+    const int nb = nblk - blk0 < C::BPS ? nblk - blk0 : C::BPS;
+    issue_stage_copies<C>(ring + slot * C::STAGE, bars + slot * 8, lane, phys, nb, kbase, vbase, p.kv_block_stride);
+  };
+  auto load_phys = [&](int st) -> int {
+    const int blk = st * C::BPS + lane;
+    return (lane < C::BPS && blk < nblk) ? __ldg(table + blk) : 0;
+  };
+  {
+    int ph[NST];
+#pragma unroll
+    for (int k = 0; k < NST; ++k) ph[k] = (warp + k * W < nstages) ? load_phys(warp + k * W) : 0;
+#pragma unroll
+    for (int k = 0; k < NST; ++k)
+      if (warp + k * W < nstages) issue_stage(warp + k * W, k, ph[k]);
+  }
+  int next_phys = (warp + NST * W < nstages) ? load_phys(warp + NST * W) : 0;
+
+  float m[G], lsum[G], acc[G][C::NJ];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY;
+    lsum[g] = 0.f;
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) acc[g][j] = 0.f;
+  }
+
+  int k = 0;
+  for (int st = warp; st < nstages; st += W, ++k) {
+    const int slot = k % NST;
+    mbar_wait(bars + slot * 8, (k / NST) & 1);
+    if (APPEND && row_owner && st == nstages - 1 && new_slot >= 0 &&
+        new_slot == phys_last * B + (r.tok_end - 1) % B) {
+      const int in_stage = (r.tok_end - 1 - r.tok_begin) - st * 32;
+      const int b = in_stage / B;
+      const int off = (int)(new_slot % B);
+      uint8_t* kt = smem + (warp * NST + slot) * C::STAGE + b * C::TILE;
+      uint8_t* vt = smem + (warp * NST + slot) * C::STAGE + (C::BPS + b) * C::TILE;
+      if (lane < D / 8) *reinterpret_cast<uint4*>(kt + (lane * B + off) * 16) = patch_k;
+#pragma unroll
+      for (int u = 0; u < (D + 63) / 64; ++u) {
+        const int i = lane + 32 * u;
+        if (i < D / 2) {
+          reinterpret_cast<uint16_t*>(vt)[(2 * i) * B + off] = (uint16_t)(patch_v[u] & 0xffffu);
+          reinterpret_cast<uint16_t*>(vt)[(2 * i + 1) * B + off] = (uint16_t)(patch_v[u] >> 16);
+        }
+      }
+      __syncwarp();
+    }
+    process_stage_gqa<C>(ring + slot * C::STAGE, pbuf, lane, qs, m, lsum, acc, r.tok_begin + st * 32, r.tok_end,
+                         p.scale_log2e);
+    const int st_next = st + NST * W;
+    if (st_next < nstages) {
+      issue_stage(st_next, slot, next_phys);
+      next_phys = (st_next + W < nstages) ? load_phys(st_next + W) : 0;
+    }
+  }
+
+  if (APPEND && row_owner && new_slot >= 0) {
+    const int64_t blk = new_slot / B;
+    const int off = (int)(new_slot % B);
+    __half* kdst = p.kc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride;
+    uint16_t* vdst =
+        reinterpret_cast<uint16_t*>(p.vc_w + blk * p.kv_block_stride + (int64_t)kv_head * p.kv_head_stride) + off;
+    if (lane < D / 8) *reinterpret_cast<uint4*>(kdst + ((int64_t)lane * B + off) * 8) = patch_k;
+#pragma unroll
+    for (int u = 0; u < (D + 63) / 64; ++u) {
+      const int i = lane + 32 * u;
+      if (i < D / 2) {
+        vdst[(int64_t)(2 * i) * B] = (uint16_t)(patch_v[u] & 0xffffu);
+        vdst[(int64_t)(2 * i + 1) * B] = (uint16_t)(patch_v[u] >> 16);
+      }
+    }
+  }
+
+  float* red = reinterpret_cast<float*>(smem + C::RED_OFF);  // [G][W][D + 2]
+#pragma unroll
+  for (int g = 0; g < G; ++g) warp_publish<C>(red + g * (W * (D + 2)), warp, lane, m[g], lsum[g], acc[g]);
+  __syncthreads();
+  for (int g = 0; g < G; ++g)
+    cta_merge_and_store<C, W, 1>(p, red + g * (W * (D + 2)), threadIdx.x, seq, head0 + g, split, r.nsplit_seq, &s_last);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Persistent kernel: grid = resident CTAs; each CTA pulls (seq, head, split) units from a global
 // ticket counter and its warps keep their bulk-copy rings full ACROSS unit boundaries, so the
 // per-unit prologue (metadata, table, first-copy latency) and epilogue (merge, store) overlap the
@@ -770,8 +1026,9 @@ struct Variant {
 // The persistent variants are kept for experiments: on B200 they measured 3-8 % SLOWER than the classic
 // grid at every BASELINE shape (profiles/r01c_persistent_vs_classic.md), so they are not the default.
 static constexpr Variant kVariants[] = {{4, 2, false}, {4, 3, false}, {8, 1, false}, {2, 2, false},
-                                        {4, 2, true},  {8, 1, true},  {4, 3, true},  {2, 2, true}};
-constexpr int kNumVariants = 8;
+                                        {4, 2, true},  {8, 1, true},  {4, 3, true},  {2, 2, true},
+                                        {4, 2, false}};  // 8: the default kernel with the grouped-query path off
+constexpr int kNumVariants = 9;
 
 template <int D, int B, int W, int NST, bool APPEND>
 static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
@@ -844,6 +1101,51 @@ static int launch_variant(const PaParams& p, int num_seqs, int variant, int* sch
   }
 }
 
+// Grouped-query launch: G query heads of one kv head per CTA.  Returns 1 if this shape has no such instantiation.
+template <int D, int B, int G, bool APPEND>
+static int launch_gqa_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
+  constexpr int W = default_warps(D);
+  using C = PaCfgG<D, B, W, 2, G>;
+  static_assert(C::FITS, "shared memory");
+  auto kern = pa_v1_gqa_kernel<D, B, W, 2, APPEND, G>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  VB200_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    VB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set[dev] = true;
+  }
+  dim3 grid(p.num_heads / G, num_seqs, p.num_splits);
+  VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
+  count_launch();
+  return VB200_OK;
+}
+template <int D, int B>
+static int launch_gqa(const PaParams& p, int num_seqs, cudaStream_t stream) {
+  const int ratio = p.num_heads / p.num_kv_heads;
+  constexpr int NJ = (D * B / 8 + 31) / 32;
+  if constexpr (4 * NJ <= 32) {  // accumulators of 4 heads fit in registers
+    if (ratio % 4 == 0)
+      return p.new_k ? launch_gqa_impl<D, B, 4, true>(p, num_seqs, stream)
+                     : launch_gqa_impl<D, B, 4, false>(p, num_seqs, stream);
+  }
+  if constexpr (2 * NJ <= 32) {
+    if (ratio % 2 == 0)
+      return p.new_k ? launch_gqa_impl<D, B, 2, true>(p, num_seqs, stream)
+                     : launch_gqa_impl<D, B, 2, false>(p, num_seqs, stream);
+  }
+  return 1;
+}
+template <int D>
+static int launch_gqa_block(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
+  switch (block_size) {
+    case 8: return launch_gqa<D, 8>(p, num_seqs, stream);
+    case 16: return launch_gqa<D, 16>(p, num_seqs, stream);
+    case 32: return launch_gqa<D, 32>(p, num_seqs, stream);
+    default: return 1;
+  }
+}
+
 template <int D>
 static int launch_block(const PaParams& p, int num_seqs, int block_size, int variant, int* sched,
                         cudaStream_t stream) {
@@ -886,7 +1188,7 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
                          int* num_splits, int* split_tokens) {
   const Variant v = kVariants[variant];
   const int64_t base = (int64_t)num_seqs * num_heads;
-  const int warps = variant == 0 ? default_warps(head_size) : v.W;
+  const int warps = (variant == 0 || variant == 8) ? default_warps(head_size) : v.W;
   const int quantum = 32 * warps;  // tokens consumed by one round of the CTA's warps
   const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
@@ -1019,6 +1321,12 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   }
   int* sched = static_cast<int*>(workspace);  // nullptr => static round-robin unit assignment
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (num_heads != num_kv_heads && variant == 0) {  // grouped-query shapes: share each landed tile among the group
+    int rc = 1;
+    if (head_size == 64) rc = launch_gqa_block<64>(p, num_seqs, block_size, s);
+    if (head_size == 128) rc = launch_gqa_block<128>(p, num_seqs, block_size, s);
+    if (rc != 1) return rc;
+  }
   switch (head_size) {
     case 64: return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
     case 128: return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
