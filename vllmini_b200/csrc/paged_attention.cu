@@ -545,6 +545,9 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
 #endif
 }
 
+template <int D>
+constexpr int default_warps_c() { return (D == 64 || D == 96 || D == 192) ? 4 : 3; }   // == default_warps(D), see there
+
 // ---------------------------------------------------------------------------------------------
 // Grouped-query variant: one CTA per (G query heads of one kv head, seq, split)
 // ---------------------------------------------------------------------------------------------
@@ -562,8 +565,15 @@ struct PaCfgG : PaCfg<D, B, W, NST> {
   static constexpr int Q_OFF = (RED_OFF + G * W * (D + 2) * 4 + 15) / 16 * 16;    // G * D halves
   static constexpr int SMEM = Q_OFF + G * D * 2;
   static constexpr bool FITS = SMEM <= 227 * 1024;
+  static constexpr int CTAS_PER_SM = FITS ? (227 * 1024) / (SMEM + 1024) : 1;   // what shared memory allows (launch bound)
   static constexpr int kG = G;
 };
+
+// CTA shape of the grouped-query kernel.  Head size 128 with 4 heads per CTA needs ~250 registers at 3 warps x 2
+// stages (2 CTAs/SM, 6 warps); 4 warps x 1 stage under a 3-CTAs/SM register bound (128 registers, 12 warps) is
+// 8-16 % faster (profiles/r01k_gqa.md).  Everything else keeps the default shape of its head size.
+template <int D, int G> struct GqaShape { static constexpr int W = default_warps_c<D>(), NST = 2; };
+template <> struct GqaShape<128, 4> { static constexpr int W = 4, NST = 1; };
 
 template <class C>
 __device__ __forceinline__ void process_stage_gqa(uint32_t sbase, uint32_t pbuf, int lane, uint32_t qs,
@@ -656,7 +666,7 @@ __device__ __forceinline__ void process_stage_gqa(uint32_t sbase, uint32_t pbuf,
 }
 
 template <int D, int B, int W, int NST, bool APPEND, int G>
-__global__ void __launch_bounds__(W * 32) pa_v1_gqa_kernel(const PaParams p) {
+__global__ void __launch_bounds__(W * 32, PaCfgG<D, B, W, NST, G>::CTAS_PER_SM) pa_v1_gqa_kernel(const PaParams p) {
   using C = PaCfgG<D, B, W, NST, G>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_last;
@@ -1104,10 +1114,11 @@ static int launch_variant(const PaParams& p, int num_seqs, int variant, int* sch
 // Grouped-query launch: G query heads of one kv head per CTA.  Returns 1 if this shape has no such instantiation.
 template <int D, int B, int G, bool APPEND>
 static int launch_gqa_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
-  constexpr int W = default_warps(D);
-  using C = PaCfgG<D, B, W, 2, G>;
+  constexpr int W = GqaShape<D, G>::W, NST = GqaShape<D, G>::NST;
+  static_assert(default_warps_c<D>() == default_warps(D), "default shape");
+  using C = PaCfgG<D, B, W, NST, G>;
   static_assert(C::FITS, "shared memory");
-  auto kern = pa_v1_gqa_kernel<D, B, W, 2, APPEND, G>;
+  auto kern = pa_v1_gqa_kernel<D, B, W, NST, APPEND, G>;
   static bool attr_set[64] = {};
   int dev = 0;
   VB200_CUDA_CHECK(cudaGetDevice(&dev));
