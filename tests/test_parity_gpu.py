@@ -668,8 +668,9 @@ def test_grouped_query_kernel_is_bit_identical_to_the_per_head_grid(D, B, KVH, r
     grouped instantiation and runs the per-head grid either way."""
     from vllmini_b200 import _native, ops
     rng = np.random.default_rng(D + B + KVH + ratio)
-    H, S = KVH * ratio, 9
-    lens = rng.integers(0, 300, size=S).astype(np.int32)
+    H = KVH * ratio
+    S = 4 * 148 // H + 2              # the grouped kernel is only chosen from 4 units per SM up (bandwidth-bound)
+    lens = rng.integers(1, 200, size=S).astype(np.int32)   # >= 1: the append part below re-writes the last token
     lens[0], lens[1] = 1, 257
     q, kc, vc, bt, sl = po.make_case(S, KVH, D, B, lens, seed=ratio, max_blocks_per_seq=int(lens.max() // B + 2))
     q = rng.standard_normal((S, H, D)).astype(np.float16)
@@ -696,3 +697,18 @@ def test_grouped_query_kernel_is_bit_identical_to_the_per_head_grid(D, B, KVH, r
     truth = c_oracle().paged_attention_v1(q, kc, vc, 0.11, bt, sl, num_kv_heads=KVH, mode="exact").astype(np.float64)
     assert_close_to_truth(outs[0].cpu().numpy(), truth, atol=1.5e-3, what="grouped-query kernel")
     assert_close_to_truth(outs[2].cpu().numpy(), truth, atol=1.5e-3, what="grouped-query kernel, split-KV")
+    # fused append through the grouped kernel == reshape_and_cache + attention (same kernel arithmetic)
+    hist = np.maximum(lens.astype(np.int64) - 1, 0)
+    lens1 = (hist + 1).astype(np.int32)
+    slots = torch.from_numpy(bt[np.arange(S), hist // B].astype(np.int64) * B + hist % B).to(dev)
+    k_new = torch.from_numpy(rng.standard_normal((S, KVH, D)).astype(np.float16)).to(dev)
+    v_new = torch.from_numpy(rng.standard_normal((S, KVH, D)).astype(np.float16)).to(dev)
+    sl1 = torch.from_numpy(lens1).to(dev)
+    kc_a, vc_a, kc_b, vc_b = t[1].clone(), t[2].clone(), t[1].clone(), t[2].clone()
+    out_a, out_b = torch.empty_like(outs[0]), torch.empty_like(outs[0])
+    msl = int(bt.shape[1]) * B
+    ops.reshape_and_cache(k_new, v_new, kc_a, vc_a, slots, "auto", 1.0)
+    ops.paged_attention_v1(out_a, t[0], kc_a, vc_a, KVH, 0.11, t[3], sl1, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    ops.paged_attention_v1_append(out_b, t[0], k_new, v_new, kc_b, vc_b, slots, KVH, 0.11, t[3], sl1, B, msl)
+    torch.cuda.synchronize()
+    assert torch.equal(kc_a, kc_b) and torch.equal(vc_a, vc_b) and torch.equal(out_a, out_b)

@@ -41,6 +41,14 @@ CONFIGS = {
     "GQA4_d128": (256, 8, 128, 16, 1024, 32),   # 32 query heads over 8 kv heads (6th entry = query heads)
     "GQA8_d128": (256, 4, 128, 16, 1024, 32),
     "GQA4_d64": (256, 3, 64, 16, 1024, 12),
+    "GQA4_d128_s1_8k": (1, 8, 128, 16, 8192, 32),     # single-stream decode, long context
+    "GQA4_d128_s8_4k": (8, 8, 128, 16, 4096, 32),
+    "GQA4_d128_s16": (16, 8, 128, 16, 2048, 32),
+    "GQA4_d128_s32": (32, 8, 128, 16, 2048, 32),
+    "GQA4_d128_s64": (64, 8, 128, 16, 1024, 32),
+    "GQA4_d128_s128": (128, 8, 128, 16, 1024, 32),
+    "GQA4_d64_s32": (32, 3, 64, 16, 2048, 12),
+    "GQA4_d64_s128": (128, 3, 64, 16, 1024, 12),
     "S1_8k": (1, 12, 64, 16, 8192),
     "S1_48": (1, 12, 64, 16, 48),        # vllmini's own serving shape: 1 sequence, <= 64 tokens (server.py:37-50)
     "S4_64": (4, 12, 64, 16, 64),

@@ -1195,11 +1195,28 @@ static bool head_size_has_variants(int d) { return d == 64 || d == 128; }
 // split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
 // merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
 // is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
+// Query heads per CTA the launch will use: 4 / 2 through the grouped-query kernel (mirrors launch_gqa), else 1.
+// The grouped kernel trades parallelism for traffic: it wins once the per-head grid is several waves deep
+// (bandwidth-bound), and loses on small batches where the launch is latency-bound and the extra CTAs of the
+// per-head grid are free (profiles/r01k_gqa.md: crossover near 3-4 units per SM).
+static int heads_per_cta(int num_seqs, int num_heads, int num_kv_heads, int head_size, int block_size, int variant,
+                         int num_sms) {
+  if (num_heads == num_kv_heads || variant != 0 || (head_size != 64 && head_size != 128)) return 1;
+  if ((int64_t)num_seqs * num_heads < 4 * (int64_t)num_sms) return 1;
+  const int ratio = num_heads / num_kv_heads;
+  const int nj = (head_size * block_size / 8 + 31) / 32;
+  if (ratio % 4 == 0 && 4 * nj <= 32) return 4;
+  if (ratio % 2 == 0 && 2 * nj <= 32) return 2;
+  return 1;
+}
+
+// `group` = query heads per CTA (heads_per_cta): the launch has num_seqs * num_heads / group units.
 static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq_len, int variant, int num_sms,
-                         int* num_splits, int* split_tokens) {
+                         int group, int* num_splits, int* split_tokens) {
   const Variant v = kVariants[variant];
-  const int64_t base = (int64_t)num_seqs * num_heads;
-  const int warps = (variant == 0 || variant == 8) ? default_warps(head_size) : v.W;
+  const int64_t base = (int64_t)num_seqs * num_heads / group;
+  int warps = (variant == 0 || variant == 8) ? default_warps(head_size) : v.W;
+  if (group == 4 && head_size == 128) warps = 4;   // GqaShape<128, 4>
   const int quantum = 32 * warps;  // tokens consumed by one round of the CTA's warps
   const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
@@ -1215,7 +1232,7 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
   int st = max_seq_len > 0 ? (max_seq_len + ns - 1) / ns : quantum;
   st = (st + quantum - 1) / quantum * quantum;
   ns = max_seq_len > 0 ? (max_seq_len + st - 1) / st : 1;
-  if (base > counter_cap) ns = 1;
+  if ((int64_t)num_seqs * num_heads > counter_cap) ns = 1;   // one counter per (sequence, query head) row
   *num_splits = ns < 1 ? 1 : ns;
   *split_tokens = st;
 }
@@ -1240,9 +1257,16 @@ extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int
   if (num_seqs <= 0 || num_heads <= 0 || !head_size_supported(head_size)) return 0;
   int variant = g_tuning.variant;
   if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
-  int ns = 1, st = 0;
-  choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), &ns, &st);
-  return workspace_bytes_for(num_seqs, num_heads, head_size, ns);
+  // num_kv_heads is not part of this query: size for whichever grouping the launch may pick
+  size_t bytes = 0;
+  for (int group = 1; group <= 4; group *= 2) {
+    if (num_heads % group != 0) continue;
+    int ns = 1, st = 0;
+    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), group, &ns, &st);
+    const size_t b = workspace_bytes_for(num_seqs, num_heads, head_size, ns);
+    bytes = b > bytes ? b : bytes;
+  }
+  return bytes;
 }
 
 namespace {
@@ -1285,6 +1309,7 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
                                                      cudaGetErrorString(guard.status));
   int variant = g_tuning.variant;
   if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
+  if (a.new_k != nullptr) variant = 0;  // the fused append lives in the default instantiations
 
   PaParams p;
   p.out = static_cast<__half*>(out);
@@ -1306,7 +1331,9 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     workspace = nullptr;  // unusable scratch: run without tickets and without split
   }
   if (workspace != nullptr && max_seq_len > 0)
-    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), &ns, &st);
+    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(),
+                 heads_per_cta(num_seqs, num_heads, num_kv_heads, head_size, block_size, variant, device_sm_count()),
+                 &ns, &st);
   if (ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
   p.num_splits = ns;
   p.split_tokens = st;
@@ -1323,7 +1350,6 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
 #ifdef VB200_TRACE
   p.trace = g_trace;
 #endif
-  if (a.new_k != nullptr) variant = 0;  // the fused append lives in the default classic instantiation
   if (ns > 1) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
     p.ws_cnt = static_cast<int32_t*>(workspace) + kSchedWords;
@@ -1332,7 +1358,8 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   }
   int* sched = static_cast<int*>(workspace);  // nullptr => static round-robin unit assignment
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (num_heads != num_kv_heads && variant == 0) {  // grouped-query shapes: share each landed tile among the group
+  if (heads_per_cta(num_seqs, num_heads, num_kv_heads, head_size, block_size, variant, device_sm_count()) > 1) {
+    // grouped-query shapes, batch large enough to be bandwidth-bound: share each landed tile among the group
     int rc = 1;
     if (head_size == 64) rc = launch_gqa_block<64>(p, num_seqs, block_size, s);
     if (head_size == 128) rc = launch_gqa_block<128>(p, num_seqs, block_size, s);
