@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 1
+#define VB200_ABI_VERSION 2
 
 enum {
   VB200_OK = 0,
@@ -61,12 +61,16 @@ enum {
  *                strides address value_cache (reference: attention_kernels.cu:402-403)
  *   scale      softmax scale (head_size ** -0.5 in vllmini, gpt2.py:13)
  *   max_seq_len upper bound on seq_lens[] (vllmini passes capacity, scheduler.py:97); used only
- *                to pick the split-KV factor
- *   workspace  optional device scratch: ticket words of the persistent kernel's dynamic unit
- *                scheduler and split-KV counters/partials; may be NULL (=> static unit assignment,
- *                no split).  16-byte aligned; must be zero-filled once before its first use; the
- *                kernel leaves it reusable; one workspace must not be shared by launches that can
- *                run concurrently.  Size from vb200_paged_attention_v1_workspace_bytes().
+ *                to pick the split-KV factor -- a seq_lens[] entry above it is still attended in
+ *                full (the last split runs to seq_len), so results never depend on the split
+ *   workspace  optional device scratch for split-KV (arrival counters + fp32 partials), used only
+ *                when the batch alone leaves SMs idle (num_seqs * num_heads <= #SMs and a long
+ *                max_seq_len); may be NULL (=> never split).  16-byte aligned; must be zero-filled
+ *                once before its first use; the kernel leaves it reusable.  The library keeps NO
+ *                state of its own: the workspace is the caller's, and one workspace must not be
+ *                shared by launches that can run concurrently (other streams) -- give each stream
+ *                its own, as vllmini_b200/ops.py and csrc/torch_shim.cpp do.  Size from
+ *                vb200_paged_attention_v1_workspace_bytes() (0 when this shape never splits).
  *   device     CUDA device ordinal the pointers live on (reference: OptionalCUDAGuard, :736)
  *   stream     cudaStream_t (reference: at::cuda::getCurrentCUDAStream(), :737)
  *
@@ -97,10 +101,41 @@ int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void
                                         int64_t kv_block_stride, int64_t kv_head_stride, float scale,
                                         void* workspace, size_t workspace_bytes, int32_t device, void* stream);
 
-/* Bytes of workspace that lets the launcher use dynamic unit scheduling (64 KiB of ticket / counter
- * words, always) and its preferred split-KV factor for this problem shape (partials, when it splits). */
+/* Bytes of workspace that lets the launcher use its preferred split-KV factor for this problem shape
+ * (64 KiB of arrival counters + the fp32 partials); 0 when the launcher would not split this shape. */
 size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
                                                 int32_t block_size, int32_t max_seq_len);
+
+/*
+ * paged_attention_v2, fp16: the reference's partitioned entry (paged_attention_cuda.cpp:27-48; host entry
+ * attention_kernels.cu:966-990, launcher :844-931, partition kernel :529-562, reduce kernel :564-669).
+ * Same result as v1, through the CALLER's scratch: the context is cut into the reference's fixed 512-token
+ * partitions, P = ceil(max_seq_len / 512) of them per (sequence, head);
+ *
+ *   exp_sums, max_logits [num_seqs, num_heads, P] fp32, tmp_out [num_seqs, num_heads, P, head_size] fp16
+ *
+ * receive, for every partition that holds at least one token of its sequence, exactly what the reference's
+ * partition kernel writes (:349-357, :484-495): the partition's max logit (scale * q.k, natural-log units), the
+ * sum of exp(logit - max) and the partition's own normalised softmax(QK^T)V; partitions beyond a sequence's
+ * length are left untouched, as in the reference (:119-122).  A second launch reduces the records into `out`
+ * (:637-668; one live partition is copied, :580-592).  No other scratch: no workspace argument, no state.
+ */
+int vb200_paged_attention_v2_f16(void* out, float* exp_sums, float* max_logits, void* tmp_out, const void* query,
+                                 const void* key_cache, const void* value_cache, const int32_t* block_tables,
+                                 const int32_t* seq_lens, int32_t num_seqs, int32_t num_heads, int32_t num_kv_heads,
+                                 int32_t head_size, int32_t block_size, int32_t max_num_blocks_per_seq,
+                                 int32_t max_seq_len, int64_t q_stride, int64_t kv_block_stride,
+                                 int64_t kv_head_stride, float scale, int32_t device, void* stream);
+
+/*
+ * Which kernel instantiation and grid a v1 / fused-append call of this shape launches on a 148-SM B200, as text:
+ * "vb200::pa_v1_kernel<64,16,4,2,0> grid=(12,256,1) block=128 smem=67088" (template arguments: head size, block
+ * size, warps, ring stages, fused append[, query heads per CTA]).  A pure function of its arguments -- touches no
+ * device; bench.py labels its roofline record with it.  (No reference counterpart.)
+ */
+int vb200_paged_attention_plan(char* buf, size_t buf_bytes, int32_t num_seqs, int32_t num_heads,
+                               int32_t num_kv_heads, int32_t head_size, int32_t block_size, int32_t max_seq_len,
+                               int32_t fused_append);
 
 /*
  * reshape_and_cache, fp16 ("auto"): scatter new K/V rows into the paged caches by slot.
@@ -145,18 +180,24 @@ int vb200_reshape_and_cache_flash_f16(const void* key, const void* value, void* 
  *   x_out[r]   = s                                [num_rows, hidden] contiguous; may alias x when x_rows is NULL
  *   ln_out[r]  = fp16((s - mean(s)) * rsqrt(var(s) + eps) * gamma + beta)     statistics in fp32
  *
- * a, x: fp16 rows of `hidden` elements, row strides a_stride / x_stride (elements); hidden % 8 == 0, <= 2048.
- * With a = wte, a_rows = token ids, x = wpe, x_rows = positions it is the embedding step.
+ * a, x: fp16 tables of a_num_rows / x_num_rows rows of `hidden` elements, row strides a_stride / x_stride
+ * (elements); hidden % 8 == 0, <= 2048.  With a = wte, a_rows = token ids, x = wpe, x_rows = positions it is the
+ * embedding step; a row index outside [0, a_num_rows) / [0, x_num_rows) traps the kernel (the eager embedding
+ * lookup it replaces raises a device assert) instead of reading out of bounds.
  */
-int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a, const int64_t* a_rows, int64_t a_stride,
-                            const void* x, const int64_t* x_rows, int64_t x_stride, const void* gamma,
-                            const void* beta, int32_t num_rows, int32_t hidden, float eps, int32_t device,
-                            void* stream);
+int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a, const int64_t* a_rows, int64_t a_num_rows,
+                            int64_t a_stride, const void* x, const int64_t* x_rows, int64_t x_num_rows,
+                            int64_t x_stride, const void* gamma, const void* beta, int32_t num_rows, int32_t hidden,
+                            float eps, int32_t device, void* stream);
 
 /* Greedy sampling for the decode driver: out[r] = argmax over x[r, 0..n) (fp16 rows, row_stride elements apart);
  * first index among equal maxima, NaN counts as the maximum (torch.argmax semantics). */
 int vb200_argmax_rows_f16(int64_t* out, const void* x, int64_t row_stride, int32_t num_rows, int32_t n,
                           int32_t device, void* stream);
+
+/* 0 when `stream` is not being captured into a CUDA graph, otherwise a non-zero id unique to that capture.  For
+ * bindings that hand out split-KV workspaces: one per (device, stream, capture) keeps concurrent launches apart. */
+uint64_t vb200_stream_capture_id(void* stream);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* vb200_last_error(void);
@@ -167,10 +208,6 @@ int32_t vb200_abi_version(void);
 /* Number of kernel launches this library has enqueued since load (all threads); used by
  * bench.py to report gpu_launches and by tests to prove the CUDA path ran. */
 uint64_t vb200_launch_count(void);
-
-/* Tuning override for benchmarking/ablation (not needed by callers): forces the split-KV factor
- * (0 = heuristic) and pipeline variant (0 = default).  Returns the previous packed value. */
-int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant);
 
 /* Programmatic dependent launch (default on): kernels are launched so that their CTAs may become resident
  * while the previous kernel on the stream drains, and block (griddepcontrol.wait) until it has completed

@@ -95,7 +95,8 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
     npools = max(2, min(6, int((1 << 30) // max(bytes_one, 1)) + 1)) if bytes_one < (1 << 30) else 2
     pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed, QH=QH) for s in range(npools)]
     outs = [torch.empty_like(p[0]) for p in pools]
-    _native.set_tuning(splits, variant)
+    if splits or variant:          # sweep knobs: needs the experiments build (VLLMINI_B200_LIB=.../lib/experiments/...)
+        _native.set_tuning(splits, variant)
     def call(i):
         q, kc, vc, bt, sl = pools[i % npools]
         if ref is None:
@@ -133,7 +134,8 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
         ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
     med = ts[len(ts) // 2]
     ab = sum(algorithmic_bytes(S, H, D, B, p[4].tolist()) for p in pools) / npools
-    _native.set_tuning(0, 0)
+    if splits or variant:
+        _native.set_tuning(0, 0)
     del pools, outs
     torch.cuda.empty_cache()
     return dict(config=name, variant=variant, splits=splits, us_median=med, us_min=ts[0], gbps=ab / med / 1e3,
@@ -143,7 +145,7 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="M,C1")
-    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--variants", default="0", help="CTA-shape variants (non-zero: experiments build only)")
     ap.add_argument("--splits", default="0")
     ap.add_argument("--ref", action="store_true", help="also time the reference's own kernel (oracle/_ref)")
     ap.add_argument("--pool-mult", type=int, default=1)

@@ -10,9 +10,11 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libvllmini_b200.so")
+# VLLMINI_B200_LIB points development tools at another build of the same library (e.g. the -DVB200_EXPERIMENTS
+# build of `python -m vllmini_b200.build --experiments`); it must still be a libvllmini_b200 with the full ABI.
+LIB_PATH = os.environ.get("VLLMINI_B200_LIB") or os.path.join(_PKG, "lib", "libvllmini_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/vllmini_b200.h one to one
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -29,12 +31,16 @@ SYMBOLS = {
     "vb200_swap_blocks": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vb200_reshape_and_cache_flash_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64,
                                                  _i32, _vp]),
-    "vb200_add_layernorm_f16": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
+    "vb200_paged_attention_v2_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
+                                            _i32, _i32, _i64, _i64, _i64, _f32, _i32, _vp]),
+    "vb200_paged_attention_plan": (_i32, [ctypes.c_char_p, _sz, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "vb200_add_layernorm_f16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _f32,
+                                       _i32, _vp]),
     "vb200_argmax_rows_f16": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "vb200_stream_capture_id": (ctypes.c_uint64, [_vp]),
     "vb200_last_error": (ctypes.c_char_p, []),
     "vb200_abi_version": (_i32, []),
     "vb200_launch_count": (ctypes.c_uint64, []),
-    "vb200_set_tuning": (_i32, [_i32, _i32]),
     "vb200_set_pdl": (_i32, [_i32]),
 }
 
@@ -80,5 +86,29 @@ def set_pdl(enable: bool) -> bool:
     return bool(load().vb200_set_pdl(1 if enable else 0))
 
 
+def plan(num_seqs: int, num_heads: int, num_kv_heads: int, head_size: int, block_size: int, max_seq_len: int,
+         fused_append: bool = False) -> str:
+    """Kernel instantiation + grid a paged_attention_v1 call of this shape launches (text; touches no device)."""
+    lib = load()
+    buf = ctypes.create_string_buffer(256)
+    rc = lib.vb200_paged_attention_plan(buf, 256, num_seqs, num_heads, num_kv_heads, head_size, block_size,
+                                        max_seq_len, 1 if fused_append else 0)
+    if rc != 0:
+        raise RuntimeError(f"vllmini_b200: {last_error()} (code {rc})")
+    return buf.value.decode()
+
+
+def has_experiments() -> bool:
+    """True for a -DVB200_EXPERIMENTS build (sweep knobs compiled in; never the shipped library)."""
+    return hasattr(load(), "vb200_debug_set_tuning")
+
+
 def set_tuning(force_num_splits: int = 0, variant: int = 0) -> int:
-    return int(load().vb200_set_tuning(int(force_num_splits), int(variant)))
+    """Sweep knobs (forced split factor, CTA-shape variant) of an experiments build; raises on the shipped library."""
+    lib = load()
+    if not has_experiments():
+        raise RuntimeError("vllmini_b200: this build has no sweep knobs; build with "
+                           "`python -m vllmini_b200.build --experiments` and point VLLMINI_B200_LIB at it")
+    fn = lib.vb200_debug_set_tuning
+    fn.restype, fn.argtypes = _i32, [_i32, _i32]
+    return int(fn(int(force_num_splits), int(variant)))

@@ -36,25 +36,40 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+EXP_LIB_PATH = os.path.join(LIB_DIR, "experiments", "libvllmini_b200.so")
+
+
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True builds the sweep variant of the library (-DVB200_EXPERIMENTS: extra CTA shapes and a forced
+    split factor behind vb200_debug_set_tuning) to lib/experiments/; tools load it through VLLMINI_B200_LIB.  The
+    shipped library is always the default build."""
+    out_path = EXP_LIB_PATH if experiments else LIB_PATH
+    if experiments:
+        deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+        if not force and os.path.isfile(out_path) and all(os.path.getmtime(d) <= os.path.getmtime(out_path) for d in deps):
+            return out_path
+    elif not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
     cmd = [
-        _nvcc(), "-shared", "-o", LIB_PATH + ".tmp",
+        _nvcc(), "-shared", "-o", out_path + ".tmp",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17",
         "-Xcompiler", "-fPIC,-O3,-Wall",
         "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
         "-t", "0",
+        # smaller fatbin (2.7 MB instead of 5.6 MB); needs an R570+ driver to load, which every sm_100 box has
+        "--compress-mode=size",
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if experiments:
+        cmd += ["-DVB200_EXPERIMENTS"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     print("+", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out_path + ".tmp", out_path)
+    return out_path
 
 
 SHIM_SRC = os.path.join(CSRC, "torch_shim.cpp")
@@ -96,7 +111,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--experiments", action="store_true", help="also build lib/experiments/ (sweep knobs)")
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose))
+    if a.experiments:
+        print(build(force=a.force, verbose=a.verbose, experiments=True))
     print(build_shim(force=a.force))
     sys.exit(0)

@@ -37,7 +37,8 @@ struct DeviceGuard {
   int prev = -1;
   bool switched = false;
   cudaError_t status = cudaSuccess;
-  explicit DeviceGuard(int device) {
+  explicit DeviceGuard(int device, bool enabled = true) {
+    if (!enabled) return;  // shape-only queries never touch the CUDA runtime
     status = cudaGetDevice(&prev);
     if (status == cudaSuccess && device >= 0 && device != prev) {
       status = cudaSetDevice(device);
@@ -155,9 +156,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 }
 
 // ---- vector loads / stores ----
-__device__ __forceinline__ uint4 ldg128(const void* p) {  // read-only data: not volatile, the compiler may batch
+// volatile + "memory": every use sits after griddep_wait() (or a barrier) and reads what the PREVIOUS kernel on the
+// stream may have written (q, the new K/V rows) -- the compiler must not hoist it above that wait.  Independent
+// loads still issue back to back; only their order relative to other memory operations is pinned.
+__device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 r;
-  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
   return r;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {

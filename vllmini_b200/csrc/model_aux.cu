@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
     add_layernorm_kernel(const __half* a, const int64_t* __restrict__ a_rows, int64_t a_stride, const __half* x,
                          const int64_t* __restrict__ x_rows, int64_t x_stride, __half* x_out, __half* ln_out,
                          const __half* __restrict__ gamma, const __half* __restrict__ beta, int num_rows, int hidden,
-                         float eps) {
+                         float eps, int64_t a_num_rows, int64_t x_num_rows) {
   griddep_launch_dependents();
   griddep_wait();
   const int lane = threadIdx.x & 31;
@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(kLnWarps * 32)
   const int nchunks = hidden >> 3;
   const int64_t ar = a_rows ? a_rows[row] : row;
   const int64_t xr = x_rows ? x_rows[row] : row;
+  // an index outside its source table (token id >= vocab, position >= n_positions) fails loudly, like the device
+  // assert of the eager embedding lookup it replaces -- never a silent out-of-bounds read
+  if (ar < 0 || ar >= a_num_rows || xr < 0 || xr >= x_num_rows) __trap();
   const uint4* ap = reinterpret_cast<const uint4*>(a + ar * a_stride);
   const uint4* xp = reinterpret_cast<const uint4*>(x + xr * x_stride);  // may alias x_out: plain loads
 
@@ -221,10 +224,12 @@ extern "C" int vb200_argmax_rows_f16(int64_t* out, const void* x, int64_t row_st
 }
 
 extern "C" int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a, const int64_t* a_rows,
-                                       int64_t a_stride, const void* x, const int64_t* x_rows, int64_t x_stride,
-                                       const void* gamma, const void* beta, int32_t num_rows, int32_t hidden,
-                                       float eps, int32_t device, void* stream) {
+                                       int64_t a_num_rows, int64_t a_stride, const void* x, const int64_t* x_rows,
+                                       int64_t x_num_rows, int64_t x_stride, const void* gamma, const void* beta,
+                                       int32_t num_rows, int32_t hidden, float eps, int32_t device, void* stream) {
   if (num_rows < 0 || hidden <= 0) return set_error(VB200_ERR_INVALID_ARGUMENT, "negative or zero size argument");
+  if ((!a_rows && a_num_rows < num_rows) || (!x_rows && x_num_rows < num_rows))
+    return set_error(VB200_ERR_INVALID_ARGUMENT, "fewer source rows than num_rows and no row index array");
   if (num_rows == 0) return VB200_OK;
   if (!x_out || !ln_out || !a || !x || !gamma || !beta)
     return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
@@ -248,7 +253,8 @@ extern "C" int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a,
 #define VB200_LN_CASE(V)                                                                                            \
   case V:                                                                                                           \
     VB200_CUDA_CHECK(launch_kernel(add_layernorm_kernel<V>, grid, block, 0, s, ah, a_rows, a_stride, xh, x_rows,    \
-                                   x_stride, xo, lo, g, b, (int)num_rows, (int)hidden, eps));                       \
+                                   x_stride, xo, lo, g, b, (int)num_rows, (int)hidden, eps, a_num_rows,           \
+                                   x_num_rows));                                                                    \
     break;
   switch (vpl) {
     VB200_LN_CASE(1)
@@ -260,7 +266,7 @@ extern "C" int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a,
     VB200_LN_CASE(7)
     default:
       VB200_CUDA_CHECK(launch_kernel(add_layernorm_kernel<8>, grid, block, 0, s, ah, a_rows, a_stride, xh, x_rows,
-                                     x_stride, xo, lo, g, b, (int)num_rows, (int)hidden, eps));
+                                     x_stride, xo, lo, g, b, (int)num_rows, (int)hidden, eps, a_num_rows, x_num_rows));
   }
 #undef VB200_LN_CASE
   count_launch();

@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "vllmini_b200.h"
 
@@ -60,6 +62,12 @@ struct PaParams {
   int64_t new_v_stride;
   __half* kc_w;
   __half* vc_w;
+  // paged_attention_v2 (vb200_paged_attention_v2_f16): grid.z = the caller's 512-token partitions; every CTA writes
+  // its partition's softmax statistics and normalised output into the CALLER's scratch tensors and a second kernel
+  // reduces them (attention_kernels.cu:349-357, 564-669).  v2_exp_sums == nullptr: v1.
+  float* v2_exp_sums;    // [num_seqs, num_heads, num_splits]
+  float* v2_max_logits;  // [num_seqs, num_heads, num_splits]
+  __half* v2_tmp_out;    // [num_seqs, num_heads, num_splits, D]
 #ifdef VB200_TRACE
   unsigned long long* trace;  // [num_ctas][4]: smid, t_start, t_first_data, t_end (globaltimer ns)
 #endif
@@ -279,6 +287,25 @@ __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const flo
   }
   const int64_t row = (int64_t)seq * p.num_heads + head;
 
+  if (p.v2_exp_sums != nullptr) {
+    // paged_attention_v2 partition record, as the reference's partition kernel leaves it (attention_kernels.cu:
+    // 349-357, 484-495): max logit in natural-log units, exp_sum = sum exp(logit - max), tmp_out = the partition's
+    // own softmax-weighted V (normalised by 1 / (exp_sum + 1e-6)), fp16.
+    const int64_t part_idx = row * p.num_splits + split;
+    const float inv = __fdividef(1.f, L + 1e-6f);
+    for (int d = tid; d < D; d += W * 32) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
+      p.v2_tmp_out[part_idx * D + d] = __float2half_rn(o * inv);
+    }
+    if (tid == 0) {
+      p.v2_max_logits[part_idx] = M * 0.69314718055994530942f;  // log2 domain -> natural log
+      p.v2_exp_sums[part_idx] = L;
+    }
+    return;
+  }
+
   if (nsplit_seq == 1) {
     // reference normaliser: 1 / (sum + 1e-6)  (attention_kernels.cu:342)
     const float inv = __fdividef(1.f, L + 1e-6f);
@@ -346,16 +373,25 @@ template <int B>
 __device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int split) {
   int len = p.seq_lens[seq];
   len = len < p.max_blocks_per_seq * B ? len : p.max_blocks_per_seq * B;  // never read past the table row
-  if (p.num_splits > 1 && len > p.num_splits * p.split_tokens) len = p.num_splits * p.split_tokens;
+  const bool v2 = p.v2_exp_sums != nullptr;
+  const bool parts = p.num_splits > 1 || v2;
+  // v2: the caller's scratch has room for num_splits partitions and no more.  v1: max_seq_len is only a hint for the
+  // split factor -- the LAST split runs to seq_len, so the result never depends on whether the launch was split.
+  if (v2 && len > p.num_splits * p.split_tokens) len = p.num_splits * p.split_tokens;
   UnitRange r;
-  r.tok_begin = p.num_splits > 1 ? split * p.split_tokens : 0;
-  r.empty_split = split > 0 && r.tok_begin >= len;
+  r.tok_begin = parts ? split * p.split_tokens : 0;
+  // nothing to do, nobody waits for it (v2: also partition 0 of an empty sequence, attention_kernels.cu:119-122)
+  r.empty_split = (split > 0 || v2) && r.tok_begin >= len;
   r.tok_end = len;
-  if (p.num_splits > 1 && r.tok_begin + p.split_tokens < len) r.tok_end = r.tok_begin + p.split_tokens;
+  if (parts && split < p.num_splits - 1 && r.tok_begin + p.split_tokens < len) r.tok_end = r.tok_begin + p.split_tokens;
   const int ntok = r.tok_end > r.tok_begin ? r.tok_end - r.tok_begin : 0;
   r.nstages = (ntok + 31) >> 5;
   r.nblk = (ntok + B - 1) / B;
-  r.nsplit_seq = p.num_splits > 1 && len > 0 ? (len + p.split_tokens - 1) / p.split_tokens : 1;
+  r.nsplit_seq = 1;
+  if (p.num_splits > 1 && len > 0) {
+    const int n = (len + p.split_tokens - 1) / p.split_tokens;
+    r.nsplit_seq = n < p.num_splits ? n : p.num_splits;
+  }
   return r;
 }
 
@@ -812,247 +848,119 @@ __global__ void __launch_bounds__(W * 32, PaCfgG<D, B, W, NST, G>::CTAS_PER_SM) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent kernel: grid = resident CTAs; each CTA pulls (seq, head, split) units from a global
-// ticket counter and its warps keep their bulk-copy rings full ACROSS unit boundaries, so the
-// per-unit prologue (metadata, table, first-copy latency) and epilogue (merge, store) overlap the
-// streaming of the next unit.  Warps 0..W-1 compute; warp W is the scheduler: lane 0 fetches
-// tickets, resolves unit metadata (seq_len load, split range) and publishes it through a ring of NU
-// shared-memory descriptors guarded by full/empty mbarriers, running up to NU units ahead.
+// paged_attention_v2: reduce over the caller's partition records (attention_kernels.cu:564-669)
 // ---------------------------------------------------------------------------------------------
-struct UnitDesc {  // 32 bytes
-  int seq, head, split, tok_begin, tok_end, nstages, nsplit_seq, valid;
-};
-constexpr int kNU = 4;
-
-template <int D, int B, int W, int NST>
-struct PaPersistCfg : PaCfg<D, B, W, NST> {
-  using Base = PaCfg<D, B, W, NST>;
-  static constexpr int RED2_OFF = Base::RED_OFF;                           // 2 x W x (D + 2) floats
-  static constexpr int UNIT_OFF = RED2_OFF + 2 * W * (D + 2) * 4;          // kNU descriptors
-  static constexpr int UBAR_OFF = UNIT_OFF + kNU * (int)sizeof(UnitDesc);  // full[kNU], empty[kNU]
-  static constexpr int SMEM = UBAR_OFF + 2 * kNU * 8 + 16;
-};
-
-template <int D, int B, int W, int NST>
-__global__ void __launch_bounds__((W + 1) * 32) pa_v1_persistent_kernel(const PaParams p, const int num_units,
-                                                                       int* __restrict__ sched) {
-  using C = PaPersistCfg<D, B, W, NST>;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-
-  UnitDesc* units = reinterpret_cast<UnitDesc*>(smem + C::UNIT_OFF);
-  const uint32_t ufull = smem_u32(smem + C::UBAR_OFF);
-  const uint32_t uempty = ufull + kNU * 8;
-  int* s_last = reinterpret_cast<int*>(smem + C::UBAR_OFF + 2 * kNU * 8);
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + C::BAR_OFF) + i * 8, 1);
-#pragma unroll
-    for (int i = 0; i < kNU; ++i) {
-      mbar_init(ufull + i * 8, 1);
-      mbar_init(uempty + i * 8, W);
-    }
-    fence_mbar_init();
-  }
+// Grid (H, S), D threads' worth of work per CTA: out = sum_j tmp_out[j] * exp_sums[j] * exp(max_logits[j] - M) /
+// (sum_j exp_sums[j] * exp(max_logits[j] - M) + 1e-6); a single live partition is copied (reference :580-592); an
+// empty sequence yields zeros (the reference's loop over zero partitions does the same).
+template <int D>
+__global__ void __launch_bounds__(128) pa_v2_reduce_kernel(__half* __restrict__ out, const float* __restrict__ exp_sums,
+                                                           const float* __restrict__ max_logits,
+                                                           const __half* __restrict__ tmp_out,
+                                                           const int32_t* __restrict__ seq_lens, int num_heads,
+                                                           int max_num_partitions, int partition_tokens,
+                                                           int max_tokens) {
+  const int head = blockIdx.x, seq = blockIdx.y;
   griddep_launch_dependents();
-  griddep_wait();
-  __syncthreads();
-
-  // =================================== scheduler warp ===================================
-  if (warp == W) {
-    if (lane != 0) return;
-    const int H = p.num_heads, ns = p.num_splits;
-    int i = 0;  // descriptors published so far
-    for (int n = 0;; ++n) {
-      const int u = sched ? atomicAdd(sched, 1) : (int)blockIdx.x + n * (int)gridDim.x;
-      UnitDesc d;
-      d.valid = u < num_units;
-      d.seq = d.head = d.split = d.tok_begin = d.tok_end = d.nstages = 0;
-      d.nsplit_seq = 1;
-      if (d.valid) {
-        d.head = u % H;
-        const int rest = u / H;
-        d.split = rest % ns;
-        d.seq = rest / ns;
-        const UnitRange r = unit_range<B>(p, d.seq, d.split);
-        if (r.empty_split) continue;  // no token in this split: skip the ticket
-        d.tok_begin = r.tok_begin;
-        d.tok_end = r.tok_end;
-        d.nstages = r.nstages;
-        d.nsplit_seq = r.nsplit_seq;
-      }
-      const int e = i % kNU;
-      if (i >= kNU) mbar_wait(uempty + e * 8, ((i / kNU) - 1) & 1);
-      units[e] = d;
-      mbar_arrive(ufull + e * 8);  // release: descriptor visible to waiters
-      ++i;
-      if (!d.valid) break;
-    }
-    if (sched) {  // last CTA to run dry re-arms the ticket counter for the next launch
-      const int done = atomicAdd(sched + 1, 1);
-      if (done == (int)gridDim.x - 1) {
-        sched[0] = 0;
-        sched[1] = 0;
-        __threadfence();
-      }
-    }
+  griddep_wait();  // the partition kernel's records
+  int len = seq_lens[seq];
+  len = len < max_tokens ? len : max_tokens;
+  int np = (len + partition_tokens - 1) / partition_tokens;
+  np = np < max_num_partitions ? np : max_num_partitions;
+  const int64_t row = (int64_t)seq * num_heads + head;
+  const float* ml = max_logits + row * max_num_partitions;
+  const float* es = exp_sums + row * max_num_partitions;
+  const __half* to = tmp_out + row * max_num_partitions * D;
+  __half* o = out + row * D;
+  if (np == 1) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = to[d];
     return;
   }
-
-  // =================================== compute warps ===================================
-  const uint32_t ring = smem_u32(smem) + warp * (NST * C::STAGE);
-  const uint32_t pbuf = smem_u32(smem + C::PBUF_OFF) + warp * 64;
-  const uint32_t bars = smem_u32(smem + C::BAR_OFF) + warp * (NST * 8);
-  float* red2 = reinterpret_cast<float*>(smem + C::RED2_OFF);
-  const int qpk = p.num_heads / p.num_kv_heads;
-
-  // producer state: unit pi (descriptor P), next stage pk of this warp's share, copies issued so far
-  int pi = -1, pk = 0, n_issued = 0, n_consumed = 0;
-  UnitDesc P;
-  P.valid = 1;
-  P.nstages = 0;
-  P.seq = P.head = P.split = P.tok_begin = P.tok_end = 0;
-  P.nsplit_seq = 1;
-  const int32_t* p_table = nullptr;
-  const __half* p_kbase = nullptr;
-  const __half* p_vbase = nullptr;
-  int p_nblk = 0;
-  int phys_pref = 0;  // table entries of P's stage pk (lane b < BPS), prefetched
-  uint4 q_next[C::NJ];
-#pragma unroll
-  for (int j = 0; j < C::NJ; ++j) q_next[j] = make_uint4(0, 0, 0, 0);
-  int ci = 0;  // consumer unit index
-
-  auto load_phys = [&](int st) -> int {
-    const int blk = st * C::BPS + lane;
-    return (lane < C::BPS && blk < p_nblk) ? __ldg(p_table + blk) : 0;
-  };
-  // move the producer to the next published unit; prefetch its q and first table entries
-  auto advance = [&]() {
-    ++pi;
-    pk = 0;
-    const int e = pi % kNU;
-    mbar_wait(ufull + e * 8, (pi / kNU) & 1);
-    P = units[e];
-    if (P.valid) {
-      const int kv_head = P.head / qpk;
-      p_table = p.block_tables + (int64_t)P.seq * p.max_blocks_per_seq + P.tok_begin / B;
-      p_kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
-      p_vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
-      const int ntok = P.tok_end - P.tok_begin;
-      p_nblk = ntok > 0 ? (ntok + B - 1) / B : 0;
-      const __half* qrow = p.q + (int64_t)P.seq * p.q_stride + (int64_t)P.head * D;
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) q_next[j] = ldg128(qrow + 8 * (lane / B + j * C::BPS));
-      phys_pref = (warp < P.nstages) ? load_phys(warp) : 0;
-    }
-  };
-  // issue at most one stage; the producer may run at most one unit ahead of the consumer
-  auto try_issue = [&]() -> bool {
-    for (;;) {
-      if (!P.valid) return false;
-      const int st = warp + pk * W;
-      if (pi >= 0 && st < P.nstages) {
-        const int blk0 = st * C::BPS;
-        const int nb = p_nblk - blk0 < C::BPS ? p_nblk - blk0 : C::BPS;
-        const int slot = n_issued % NST;
-        issue_stage_copies<C>(ring + slot * C::STAGE, bars + slot * 8, lane, phys_pref, nb, p_kbase, p_vbase,
-                              p.kv_block_stride);
-        ++n_issued;
-        ++pk;
-        const int st2 = warp + pk * W;
-        if (st2 < P.nstages) {
-          phys_pref = load_phys(st2);
-        } else if (pi <= ci) {
-          advance();  // share of this unit fully issued: step into the next unit right away
-        }
-        return true;
-      }
-      if (pi > ci) return false;  // already one unit ahead of the consumer
-      advance();
-    }
-  };
-
-  advance();  // pi = 0
-  for (;;) {
-    // ---- consumer enters unit ci (the producer is in it too: pi == ci here) ----
-    while (pi < ci) advance();
-    const UnitDesc U = P;
-    if (!U.valid) break;
-    uint4 qv[C::NJ];
-#pragma unroll
-    for (int j = 0; j < C::NJ; ++j) qv[j] = q_next[j];
-    if (lane == 0) mbar_arrive(uempty + (ci % kNU) * 8);  // this warp holds its own copy of the descriptor
-    while (n_issued - n_consumed < NST && try_issue()) {
-    }
-
-    float m = -INFINITY, lsum = 0.f;
-    float acc[C::NJ];
-#pragma unroll
-    for (int j = 0; j < C::NJ; ++j) acc[j] = 0.f;
-
-    for (int st = warp; st < U.nstages; st += W) {
-      const int slot = n_consumed % NST;
-      mbar_wait(bars + slot * 8, (n_consumed / NST) & 1);
-      process_stage<C>(ring + slot * C::STAGE, pbuf, lane, qv, 0u, m, lsum, acc, U.tok_begin + st * 32, U.tok_end,
-                       p.scale_log2e);
-      ++n_consumed;
-      try_issue();
-    }
-
-    float* red = red2 + (ci & 1) * (W * (D + 2));
-    warp_publish<C>(red, warp, lane, m, lsum, acc);
-    named_bar_sync<1, W * 32>();
-    cta_merge_and_store<C, W, 2>(p, red, threadIdx.x, U.seq, U.head, U.split, U.nsplit_seq, s_last);
-    ++ci;
+  float M = -INFINITY;
+  for (int j = 0; j < np; ++j) M = fmaxf(M, ld_cg_f32(ml + j));
+  float G = 0.f;
+  for (int j = 0; j < np; ++j) G += ld_cg_f32(es + j) * __expf(ld_cg_f32(ml + j) - M);
+  const float inv = __fdividef(1.f, G + 1e-6f);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < np; ++j)
+      acc += __half2float(to[(int64_t)j * D + d]) * (ld_cg_f32(es + j) * __expf(ld_cg_f32(ml + j) - M)) * inv;
+    o[d] = __float2half_rn(acc);
   }
 }
 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
-constexpr int kCounterCap = 16384;  // int32 words at the start of the workspace: [0..15] scheduler, rest split counters
-constexpr int kSchedWords = 16;
+constexpr int kCounterCap = 16384;     // int32 split-KV arrival counters at the start of the workspace (one per row)
+constexpr int kV2PartitionTokens = 512;  // PARTITION_SIZE of the reference's v2 launcher (attention_kernels.cu:847)
 
 #ifdef VB200_TRACE
 static unsigned long long* g_trace = nullptr;
 extern "C" void vb200_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
 #endif
 
+// CTA shape: W warps x NST ring stages.  The shipped library has ONE shape per head size (default_warps(D) x 2);
+// a -DVB200_EXPERIMENTS build adds the other shapes and a forced split factor for sweeps (tools/sweep.py), set
+// through vb200_debug_set_tuning -- not declared in the public header, not present in the default build.
+struct Shape {
+  int W, NST;
+};
+#ifdef VB200_EXPERIMENTS
 struct Tuning {
   int force_splits = 0;
   int variant = 0;
 };
 static Tuning g_tuning;
+// 0: default; 1: 4x3; 2: 8x1; 3: 2x2; 4: default kernel with the grouped-query path off
+static constexpr Shape kVariants[] = {{0, 2}, {4, 3}, {8, 1}, {2, 2}, {0, 2}};
+constexpr int kNumVariants = 5;
+static int tuning_variant() { return g_tuning.variant; }
+static int tuning_force_splits() { return g_tuning.force_splits; }
+#else
+static constexpr int tuning_variant() { return 0; }
+static constexpr int tuning_force_splits() { return 0; }
+#endif
 
-struct Variant {
-  int W, NST;
-  bool persistent;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): a lock-free
+// test-and-set per device (the attribute call itself is idempotent, so two racing first callers are harmless).
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  template <class F>
+  cudaError_t run(int dev, F&& f) {
+    if (dev < 0 || dev >= 64) return f();
+    const uint64_t bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = f();
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
 };
-// 0 (default): classic grid (H, S, splits), default_warps(D) warps x 2 stages; 1: classic 4x3; 2: classic 8x1; 3: classic 2x2;
-// 4: persistent 4x2 (+1 scheduler warp); 5: persistent 8x1; 6: persistent 4x3; 7: persistent 2x2.
-// The persistent variants are kept for experiments: on B200 they measured 3-8 % SLOWER than the classic
-// grid at every BASELINE shape (profiles/r01c_persistent_vs_classic.md), so they are not the default.
-static constexpr Variant kVariants[] = {{4, 2, false}, {4, 3, false}, {8, 1, false}, {2, 2, false},
-                                        {4, 2, true},  {8, 1, true},  {4, 3, true},  {2, 2, true},
-                                        {4, 2, false}};  // 8: the default kernel with the grouped-query path off
-constexpr int kNumVariants = 9;
+
+// what a launch did, for vb200_paged_attention_plan (a pure function of the problem shape)
+struct Plan {
+  const char* kernel = "";
+  int D = 0, B = 0, W = 0, NST = 0, G = 1, append = 0;
+  unsigned gx = 0, gy = 0, gz = 0;
+  int smem = 0;
+};
 
 template <int D, int B, int W, int NST, bool APPEND>
-static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
+static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t stream, Plan* plan) {
   using C = PaCfg<D, B, W, NST>;
   static_assert(C::FITS, "shared memory");
   auto kern = pa_v1_kernel<D, B, W, NST, APPEND>;
-  static bool attr_set[64] = {};
+  dim3 grid(p.num_heads, num_seqs, p.num_splits);
+  if (plan) {
+    *plan = Plan{"pa_v1_kernel", D, B, W, NST, 1, APPEND, grid.x, grid.y, grid.z, C::SMEM};
+    return VB200_OK;
+  }
+  static DeviceOnce once;
   int dev = 0;
   VB200_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    VB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set[dev] = true;
-  }
-  dim3 grid(p.num_heads, num_seqs, p.num_splits);
+  VB200_CUDA_CHECK(once.run(dev, [&] {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  }));
   VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
   count_launch();
   return VB200_OK;
@@ -1066,135 +974,94 @@ constexpr int default_warps(int head_size) {
 }
 
 template <int D, int B, int W, int NST>
-static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream) {
+static int launch_classic(const PaParams& p, int num_seqs, cudaStream_t stream, Plan* plan) {
   if (p.new_k != nullptr) {  // the fused append lives in the default instantiation of each head size
-    if constexpr (W == default_warps(D) && NST == 2) return launch_classic_impl<D, B, W, 2, true>(p, num_seqs, stream);
+    if constexpr (W == default_warps(D) && NST == 2)
+      return launch_classic_impl<D, B, W, 2, true>(p, num_seqs, stream, plan);
   }
-  return launch_classic_impl<D, B, W, NST, false>(p, num_seqs, stream);
-}
-
-template <int D, int B, int W, int NST>
-static int launch_persistent(const PaParams& p, int num_seqs, int* sched, cudaStream_t stream) {
-  using C = PaPersistCfg<D, B, W, NST>;
-  auto kern = pa_v1_persistent_kernel<D, B, W, NST>;
-  constexpr int kThreads = (W + 1) * 32;
-  static int resident[64] = {};  // CTAs that fit on the device at once (0 = not yet queried)
-  int dev = 0;
-  VB200_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return set_error(VB200_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", dev);
-  if (resident[dev] == 0) {
-    VB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    int per_sm = 0;
-    VB200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, C::SMEM));
-    if (per_sm < 1) return set_error(VB200_ERR_CUDA, "persistent kernel does not fit on an SM");
-    resident[dev] = per_sm * device_sm_count();
-  }
-  const long long num_units = (long long)num_seqs * p.num_heads * p.num_splits;
-  if (num_units > 0x7fffffffLL - 65536) return set_error(VB200_ERR_INVALID_ARGUMENT, "too many work units");
-  const int grid = num_units < resident[dev] ? (int)num_units : resident[dev];
-  VB200_CUDA_CHECK(launch_kernel(kern, dim3(grid), dim3(kThreads), (size_t)C::SMEM, stream, p, (int)num_units, sched));
-  count_launch();
-  return VB200_OK;
+  return launch_classic_impl<D, B, W, NST, false>(p, num_seqs, stream, plan);
 }
 
 template <int D, int B>
-static int launch_variant(const PaParams& p, int num_seqs, int variant, int* sched, cudaStream_t stream) {
-  switch (variant) {
-    case 1: return launch_classic<D, B, 4, 3>(p, num_seqs, stream);
-    case 2: return launch_classic<D, B, 8, 1>(p, num_seqs, stream);
-    case 3: return launch_classic<D, B, 2, 2>(p, num_seqs, stream);
-    case 4: return launch_persistent<D, B, 4, 2>(p, num_seqs, sched, stream);
-    case 5: return launch_persistent<D, B, 8, 1>(p, num_seqs, sched, stream);
-    case 6: return launch_persistent<D, B, 4, 3>(p, num_seqs, sched, stream);
-    case 7: return launch_persistent<D, B, 2, 2>(p, num_seqs, sched, stream);
-    default: return launch_classic<D, B, default_warps(D), 2>(p, num_seqs, stream);
+static int launch_variant(const PaParams& p, int num_seqs, int variant, cudaStream_t stream, Plan* plan) {
+#ifdef VB200_EXPERIMENTS
+  if constexpr (D == 64 || D == 128) {
+    switch (variant) {
+      case 1: return launch_classic<D, B, 4, 3>(p, num_seqs, stream, plan);
+      case 2: return launch_classic<D, B, 8, 1>(p, num_seqs, stream, plan);
+      case 3: return launch_classic<D, B, 2, 2>(p, num_seqs, stream, plan);
+      default: break;
+    }
   }
+#endif
+  (void)variant;
+  return launch_classic<D, B, default_warps(D), 2>(p, num_seqs, stream, plan);
 }
 
 // Grouped-query launch: G query heads of one kv head per CTA.  Returns 1 if this shape has no such instantiation.
 template <int D, int B, int G, bool APPEND>
-static int launch_gqa_impl(const PaParams& p, int num_seqs, cudaStream_t stream) {
+static int launch_gqa_impl(const PaParams& p, int num_seqs, cudaStream_t stream, Plan* plan) {
   constexpr int W = GqaShape<D, G>::W, NST = GqaShape<D, G>::NST;
   static_assert(default_warps_c<D>() == default_warps(D), "default shape");
   using C = PaCfgG<D, B, W, NST, G>;
   static_assert(C::FITS, "shared memory");
   auto kern = pa_v1_gqa_kernel<D, B, W, NST, APPEND, G>;
-  static bool attr_set[64] = {};
+  dim3 grid(p.num_heads / G, num_seqs, p.num_splits);
+  if (plan) {
+    *plan = Plan{"pa_v1_gqa_kernel", D, B, W, NST, G, APPEND, grid.x, grid.y, grid.z, C::SMEM};
+    return VB200_OK;
+  }
+  static DeviceOnce once;
   int dev = 0;
   VB200_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    VB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set[dev] = true;
-  }
-  dim3 grid(p.num_heads / G, num_seqs, p.num_splits);
+  VB200_CUDA_CHECK(once.run(dev, [&] {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  }));
   VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
   count_launch();
   return VB200_OK;
 }
 template <int D, int B>
-static int launch_gqa(const PaParams& p, int num_seqs, cudaStream_t stream) {
+static int launch_gqa(const PaParams& p, int num_seqs, cudaStream_t stream, Plan* plan) {
   const int ratio = p.num_heads / p.num_kv_heads;
   constexpr int NJ = (D * B / 8 + 31) / 32;
   if constexpr (4 * NJ <= 32) {  // accumulators of 4 heads fit in registers
     if (ratio % 4 == 0)
-      return p.new_k ? launch_gqa_impl<D, B, 4, true>(p, num_seqs, stream)
-                     : launch_gqa_impl<D, B, 4, false>(p, num_seqs, stream);
+      return p.new_k ? launch_gqa_impl<D, B, 4, true>(p, num_seqs, stream, plan)
+                     : launch_gqa_impl<D, B, 4, false>(p, num_seqs, stream, plan);
   }
   if constexpr (2 * NJ <= 32) {
     if (ratio % 2 == 0)
-      return p.new_k ? launch_gqa_impl<D, B, 2, true>(p, num_seqs, stream)
-                     : launch_gqa_impl<D, B, 2, false>(p, num_seqs, stream);
+      return p.new_k ? launch_gqa_impl<D, B, 2, true>(p, num_seqs, stream, plan)
+                     : launch_gqa_impl<D, B, 2, false>(p, num_seqs, stream, plan);
   }
   return 1;
 }
 template <int D>
-static int launch_gqa_block(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
+static int launch_gqa_block(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream, Plan* plan) {
   switch (block_size) {
-    case 8: return launch_gqa<D, 8>(p, num_seqs, stream);
-    case 16: return launch_gqa<D, 16>(p, num_seqs, stream);
-    case 32: return launch_gqa<D, 32>(p, num_seqs, stream);
+    case 8: return launch_gqa<D, 8>(p, num_seqs, stream, plan);
+    case 16: return launch_gqa<D, 16>(p, num_seqs, stream, plan);
+    case 32: return launch_gqa<D, 32>(p, num_seqs, stream, plan);
     default: return 1;
   }
 }
 
 template <int D>
-static int launch_block(const PaParams& p, int num_seqs, int block_size, int variant, int* sched,
-                        cudaStream_t stream) {
+static int launch_block(const PaParams& p, int num_seqs, int block_size, int variant, cudaStream_t stream,
+                        Plan* plan) {
   switch (block_size) {
-    case 8: return launch_variant<D, 8>(p, num_seqs, variant, sched, stream);
-    case 16: return launch_variant<D, 16>(p, num_seqs, variant, sched, stream);
-    case 32: return launch_variant<D, 32>(p, num_seqs, variant, sched, stream);
+    case 8: return launch_variant<D, 8>(p, num_seqs, variant, stream, plan);
+    case 16: return launch_variant<D, 16>(p, num_seqs, variant, stream, plan);
+    case 32: return launch_variant<D, 32>(p, num_seqs, variant, stream, plan);
     default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
   }
-}
-
-// The reference's other head sizes (attention_kernels.cu:738-766: 80, 96, 112, 192, 256): default shape only.
-template <int D, int W, int NST>
-static int launch_block_shape(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
-  if constexpr (PaCfg<D, 16, W, NST>::FITS) {
-    switch (block_size) {
-      case 8: return launch_classic<D, 8, W, NST>(p, num_seqs, stream);
-      case 16: return launch_classic<D, 16, W, NST>(p, num_seqs, stream);
-      case 32: return launch_classic<D, 32, W, NST>(p, num_seqs, stream);
-      default: return set_error(VB200_ERR_BLOCK_SIZE, "Unsupported block size: %d", block_size);
-    }
-  } else {
-    return set_error(VB200_ERR_UNSUPPORTED, "shape %dx%d does not fit at head size %d", W, NST, D);
-  }
-}
-template <int D>
-static int launch_block_default(const PaParams& p, int num_seqs, int block_size, cudaStream_t stream) {
-  return launch_block_shape<D, default_warps(D), 2>(p, num_seqs, block_size, stream);
 }
 
 static bool head_size_supported(int d) {  // the reference launcher's switch, attention_kernels.cu:738-766
   return d == 64 || d == 80 || d == 96 || d == 112 || d == 128 || d == 192 || d == 256;
 }
-static bool head_size_has_variants(int d) { return d == 64 || d == 128; }
 
-// split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
-// merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
-// is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
 // Query heads per CTA the launch will use: 4 / 2 through the grouped-query kernel (mirrors launch_gqa), else 1.
 // The grouped kernel trades parallelism for traffic: it wins once the per-head grid is several waves deep
 // (bandwidth-bound), and loses on small batches where the launch is latency-bound and the extra CTAs of the
@@ -1210,18 +1077,23 @@ static int heads_per_cta(int num_seqs, int num_heads, int num_kv_heads, int head
   return 1;
 }
 
+// split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
+// merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
+// is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
 // `group` = query heads per CTA (heads_per_cta): the launch has num_seqs * num_heads / group units.
 static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq_len, int variant, int num_sms,
                          int group, int* num_splits, int* split_tokens) {
-  const Variant v = kVariants[variant];
   const int64_t base = (int64_t)num_seqs * num_heads / group;
-  int warps = (variant == 0 || variant == 8) ? default_warps(head_size) : v.W;
+  int warps = default_warps(head_size);
+#ifdef VB200_EXPERIMENTS
+  if (kVariants[variant].W) warps = kVariants[variant].W;
+#endif
+  (void)variant;
   if (group == 4 && head_size == 128) warps = 4;   // GqaShape<128, 4>
   const int quantum = 32 * warps;  // tokens consumed by one round of the CTA's warps
-  const int counter_cap = kCounterCap - kSchedWords;
   int ns = 1;
-  if (g_tuning.force_splits > 0) {
-    ns = g_tuning.force_splits;
+  if (tuning_force_splits() > 0) {
+    ns = tuning_force_splits();
   } else if (base > 0 && base <= num_sms) {
     ns = (int)((2 * (int64_t)num_sms + base - 1) / base);
     const int max_by_len = max_seq_len / 256;
@@ -1232,19 +1104,16 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
   int st = max_seq_len > 0 ? (max_seq_len + ns - 1) / ns : quantum;
   st = (st + quantum - 1) / quantum * quantum;
   ns = max_seq_len > 0 ? (max_seq_len + st - 1) / st : 1;
-  if ((int64_t)num_seqs * num_heads > counter_cap) ns = 1;   // one counter per (sequence, query head) row
+  if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;   // one counter per (sequence, query head) row
   *num_splits = ns < 1 ? 1 : ns;
   *split_tokens = st;
 }
 
-// workspace = [kCounterCap int32: scheduler words + split counters][ml: rows*2 f32][o: rows*D f32]
+// workspace = [kCounterCap int32 split counters][ml: rows*2 f32][o: rows*D f32]; nothing when the launch is not split
 static size_t workspace_bytes_for(int num_seqs, int num_heads, int head_size, int num_splits) {
-  size_t bytes = (size_t)kCounterCap * 4;  // tickets of the persistent scheduler live here even without split
-  if (num_splits > 1) {
-    const size_t rows = (size_t)num_seqs * num_heads * num_splits;
-    bytes += rows * 2 * 4 + rows * head_size * 4;
-  }
-  return bytes;
+  if (num_splits <= 1) return 0;
+  const size_t rows = (size_t)num_seqs * num_heads * num_splits;
+  return (size_t)kCounterCap * 4 + rows * 2 * 4 + rows * head_size * 4;
 }
 
 }  // namespace vb200
@@ -1255,8 +1124,7 @@ extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int
                                                            int32_t block_size, int32_t max_seq_len) {
   (void)block_size;
   if (num_seqs <= 0 || num_heads <= 0 || !head_size_supported(head_size)) return 0;
-  int variant = g_tuning.variant;
-  if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
+  int variant = tuning_variant();
   // num_kv_heads is not part of this query: size for whichever grouping the launch may pick
   size_t bytes = 0;
   for (int group = 1; group <= 4; group *= 2) {
@@ -1270,11 +1138,18 @@ extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int
 }
 
 namespace {
-struct AppendArgs {
+struct ExtraArgs {
+  // fused append
   const void* new_k = nullptr;
   const void* new_v = nullptr;
   const int64_t* slot_mapping = nullptr;
   int64_t new_k_stride = 0, new_v_stride = 0;
+  // paged_attention_v2 scratch
+  float* v2_exp_sums = nullptr;
+  float* v2_max_logits = nullptr;
+  void* v2_tmp_out = nullptr;
+  // plan query instead of a launch
+  Plan* plan = nullptr;
 };
 }  // namespace
 
@@ -1283,7 +1158,9 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
                                 int32_t num_heads, int32_t num_kv_heads, int32_t head_size, int32_t block_size,
                                 int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
                                 int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
-                                size_t workspace_bytes, int32_t device, void* stream, const AppendArgs& a) {
+                                size_t workspace_bytes, int32_t device, void* stream, const ExtraArgs& a) {
+  const bool planning = a.plan != nullptr;
+  const bool v2 = a.v2_exp_sums != nullptr;
   if (num_seqs < 0 || num_heads <= 0 || num_kv_heads <= 0 || max_num_blocks_per_seq < 0)
     return set_error(VB200_ERR_INVALID_ARGUMENT, "negative or zero size argument");
   if (block_size != 8 && block_size != 16 && block_size != 32)
@@ -1293,23 +1170,26 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     return set_error(VB200_ERR_INVALID_ARGUMENT, "num_heads %d not a multiple of num_kv_heads %d", num_heads,
                      num_kv_heads);
   if (num_seqs == 0) return VB200_OK;
-  if (!out || !query || !key_cache || !value_cache || !block_tables || !seq_lens)
-    return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
   if (num_seqs > 65535) return set_error(VB200_ERR_INVALID_ARGUMENT, "num_seqs %d exceeds grid.y limit", num_seqs);
-  // 16-byte vector / bulk-copy alignment (the reference's vector loads assume the same)
-  if (((uintptr_t)query | (uintptr_t)key_cache | (uintptr_t)value_cache) & 15)
-    return set_error(VB200_ERR_INVALID_ARGUMENT, "query/key_cache/value_cache must be 16-byte aligned");
-  if ((q_stride % 8) || (kv_block_stride % 8) || (kv_head_stride % 8))
-    return set_error(VB200_ERR_INVALID_ARGUMENT, "strides must be multiples of 8 elements (16 bytes)");
-  if (kv_head_stride < (int64_t)head_size * block_size)
-    return set_error(VB200_ERR_INVALID_ARGUMENT, "kv_head_stride smaller than one (block, head) tile");
+  if (!planning) {
+    if (!out || !query || !key_cache || !value_cache || !block_tables || !seq_lens)
+      return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
+    // 16-byte vector / bulk-copy alignment (the reference's vector loads assume the same)
+    if (((uintptr_t)query | (uintptr_t)key_cache | (uintptr_t)value_cache) & 15)
+      return set_error(VB200_ERR_INVALID_ARGUMENT, "query/key_cache/value_cache must be 16-byte aligned");
+    if ((q_stride % 8) || (kv_block_stride % 8) || (kv_head_stride % 8))
+      return set_error(VB200_ERR_INVALID_ARGUMENT, "strides must be multiples of 8 elements (16 bytes)");
+    if (kv_head_stride < (int64_t)head_size * block_size)
+      return set_error(VB200_ERR_INVALID_ARGUMENT, "kv_head_stride smaller than one (block, head) tile");
+  }
 
-  DeviceGuard guard(device);
+  DeviceGuard guard(device, /*enabled=*/!planning);
   if (guard.status != cudaSuccess) return set_error(VB200_ERR_CUDA, "cudaSetDevice(%d): %s", device,
                                                      cudaGetErrorString(guard.status));
-  int variant = g_tuning.variant;
-  if (variant < 0 || variant >= kNumVariants || !head_size_has_variants(head_size)) variant = 0;
-  if (a.new_k != nullptr) variant = 0;  // the fused append lives in the default instantiations
+  int variant = tuning_variant();
+  if (a.new_k != nullptr || v2) variant = 0;  // the fused append and v2 live in the default instantiations
+  const int num_sms = planning ? 148 : device_sm_count();
+  const int group = v2 ? 1 : heads_per_cta(num_seqs, num_heads, num_kv_heads, head_size, block_size, variant, num_sms);
 
   PaParams p;
   p.out = static_cast<__half*>(out);
@@ -1327,14 +1207,20 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.kv_head_stride = kv_head_stride;
   p.scale_log2e = (float)((double)scale * 1.4426950408889634074);
   int ns = 1, st = 0;
-  if (workspace != nullptr && (((uintptr_t)workspace & 15) || workspace_bytes < (size_t)kCounterCap * 4)) {
-    workspace = nullptr;  // unusable scratch: run without tickets and without split
+  if (v2) {
+    // the reference's fixed 512-token partitions; the partition count is the scratch tensors' stride
+    // (max_num_partitions = ceil(max_seq_len / 512), attention_kernels.cu:885)
+    st = kV2PartitionTokens;
+    ns = (max_seq_len + st - 1) / st;
+    if (ns < 1) ns = 1;
+    if (ns > 65535) return set_error(VB200_ERR_INVALID_ARGUMENT, "max_seq_len %d exceeds grid.z limit", max_seq_len);
+  } else {
+    if (!planning && workspace != nullptr && (((uintptr_t)workspace & 15) || workspace_bytes < (size_t)kCounterCap * 4))
+      workspace = nullptr;  // unusable scratch: run without split
+    if ((planning || workspace != nullptr) && max_seq_len > 0)
+      choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, group, &ns, &st);
+    if (!planning && ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
   }
-  if (workspace != nullptr && max_seq_len > 0)
-    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(),
-                 heads_per_cta(num_seqs, num_heads, num_kv_heads, head_size, block_size, variant, device_sm_count()),
-                 &ns, &st);
-  if (ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
   p.num_splits = ns;
   p.split_tokens = st;
   p.ws_cnt = nullptr;
@@ -1347,33 +1233,58 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.new_v_stride = a.new_v_stride;
   p.kc_w = static_cast<__half*>(const_cast<void*>(key_cache));
   p.vc_w = static_cast<__half*>(const_cast<void*>(value_cache));
+  p.v2_exp_sums = a.v2_exp_sums;
+  p.v2_max_logits = a.v2_max_logits;
+  p.v2_tmp_out = static_cast<__half*>(a.v2_tmp_out);
 #ifdef VB200_TRACE
   p.trace = g_trace;
 #endif
-  if (ns > 1) {
+  if (ns > 1 && !v2 && !planning) {
     const size_t rows = (size_t)num_seqs * num_heads * ns;
-    p.ws_cnt = static_cast<int32_t*>(workspace) + kSchedWords;
+    p.ws_cnt = static_cast<int32_t*>(workspace);
     p.ws_ml = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (size_t)kCounterCap * 4);
     p.ws_o = p.ws_ml + rows * 2;
   }
-  int* sched = static_cast<int*>(workspace);  // nullptr => static round-robin unit assignment
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (heads_per_cta(num_seqs, num_heads, num_kv_heads, head_size, block_size, variant, device_sm_count()) > 1) {
+  if (group > 1) {
     // grouped-query shapes, batch large enough to be bandwidth-bound: share each landed tile among the group
     int rc = 1;
-    if (head_size == 64) rc = launch_gqa_block<64>(p, num_seqs, block_size, s);
-    if (head_size == 128) rc = launch_gqa_block<128>(p, num_seqs, block_size, s);
+    if (head_size == 64) rc = launch_gqa_block<64>(p, num_seqs, block_size, s, a.plan);
+    if (head_size == 128) rc = launch_gqa_block<128>(p, num_seqs, block_size, s, a.plan);
     if (rc != 1) return rc;
   }
+  int rc;
   switch (head_size) {
-    case 64: return launch_block<64>(p, num_seqs, block_size, variant, sched, s);
-    case 128: return launch_block<128>(p, num_seqs, block_size, variant, sched, s);
-    case 80: return launch_block_default<80>(p, num_seqs, block_size, s);
-    case 96: return launch_block_default<96>(p, num_seqs, block_size, s);
-    case 112: return launch_block_default<112>(p, num_seqs, block_size, s);
-    case 192: return launch_block_default<192>(p, num_seqs, block_size, s);
-    default: return launch_block_default<256>(p, num_seqs, block_size, s);
+    case 64: rc = launch_block<64>(p, num_seqs, block_size, variant, s, a.plan); break;
+    case 128: rc = launch_block<128>(p, num_seqs, block_size, variant, s, a.plan); break;
+    case 80: rc = launch_block<80>(p, num_seqs, block_size, variant, s, a.plan); break;
+    case 96: rc = launch_block<96>(p, num_seqs, block_size, variant, s, a.plan); break;
+    case 112: rc = launch_block<112>(p, num_seqs, block_size, variant, s, a.plan); break;
+    case 192: rc = launch_block<192>(p, num_seqs, block_size, variant, s, a.plan); break;
+    default: rc = launch_block<256>(p, num_seqs, block_size, variant, s, a.plan); break;
   }
+  if (rc != VB200_OK || !v2 || planning) return rc;
+
+  // ---- v2: reduce the partition records into `out` (second launch; PDL lets it become resident early) ----
+  const int max_tokens = max_num_blocks_per_seq * block_size;
+  auto reduce = [&](auto kern) -> cudaError_t {
+    return launch_kernel(kern, dim3(num_heads, num_seqs), dim3(128), 0, s, static_cast<__half*>(out),
+                         static_cast<const float*>(a.v2_exp_sums), static_cast<const float*>(a.v2_max_logits),
+                         static_cast<const __half*>(a.v2_tmp_out), seq_lens, (int)num_heads, ns, st, max_tokens);
+  };
+  cudaError_t e;
+  switch (head_size) {
+    case 64: e = reduce(pa_v2_reduce_kernel<64>); break;
+    case 80: e = reduce(pa_v2_reduce_kernel<80>); break;
+    case 96: e = reduce(pa_v2_reduce_kernel<96>); break;
+    case 112: e = reduce(pa_v2_reduce_kernel<112>); break;
+    case 128: e = reduce(pa_v2_reduce_kernel<128>); break;
+    case 192: e = reduce(pa_v2_reduce_kernel<192>); break;
+    default: e = reduce(pa_v2_reduce_kernel<256>); break;
+  }
+  VB200_CUDA_CHECK(e);
+  count_launch();
+  return VB200_OK;
 }
 
 extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache,
@@ -1386,7 +1297,7 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
   return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
                               num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
                               kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream,
-                              AppendArgs{});
+                              ExtraArgs{});
 }
 
 extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
@@ -1403,7 +1314,7 @@ extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query,
     return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
   if ((((uintptr_t)key | (uintptr_t)value) & 15) || (key_stride % 8) || (value_stride % 8))
     return set_error(VB200_ERR_INVALID_ARGUMENT, "key/value rows must be 16-byte aligned");
-  AppendArgs a;
+  ExtraArgs a;
   a.new_k = key;
   a.new_v = value;
   a.slot_mapping = slot_mapping;
@@ -1414,9 +1325,54 @@ extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query,
                               kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream, a);
 }
 
-extern "C" int32_t vb200_set_tuning(int32_t force_num_splits, int32_t variant) {
+extern "C" int vb200_paged_attention_v2_f16(void* out, float* exp_sums, float* max_logits, void* tmp_out,
+                                            const void* query, const void* key_cache, const void* value_cache,
+                                            const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
+                                            int32_t num_heads, int32_t num_kv_heads, int32_t head_size,
+                                            int32_t block_size, int32_t max_num_blocks_per_seq, int32_t max_seq_len,
+                                            int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+                                            float scale, int32_t device, void* stream) {
+  if (num_seqs > 0 && (!exp_sums || !max_logits || !tmp_out))
+    return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
+  if (max_seq_len <= 0) return set_error(VB200_ERR_INVALID_ARGUMENT, "max_seq_len must be positive");
+  ExtraArgs a;
+  a.v2_exp_sums = exp_sums;
+  a.v2_max_logits = max_logits;
+  a.v2_tmp_out = tmp_out;
+  return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
+                              num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
+                              kv_block_stride, kv_head_stride, scale, nullptr, 0, device, stream, a);
+}
+
+extern "C" int vb200_paged_attention_plan(char* buf, size_t buf_bytes, int32_t num_seqs, int32_t num_heads,
+                                          int32_t num_kv_heads, int32_t head_size, int32_t block_size,
+                                          int32_t max_seq_len, int32_t fused_append) {
+  if (!buf || buf_bytes == 0) return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
+  buf[0] = 0;
+  Plan plan;
+  ExtraArgs a;
+  a.plan = &plan;
+  static const int dummy = 0;
+  if (fused_append) a.new_k = &dummy;   // selects the APPEND instantiation; never dereferenced while planning
+  const int rc = paged_attention_impl(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, num_seqs, num_heads,
+                                      num_kv_heads, head_size, block_size, 0, max_seq_len, 0, 0, 0, 1.f, nullptr, 0,
+                                      -1, nullptr, a);
+  if (rc != VB200_OK) return rc;
+  if (plan.G > 1)
+    snprintf(buf, buf_bytes, "vb200::%s<%d,%d,%d,%d,%d,%d> grid=(%u,%u,%u) block=%d smem=%d", plan.kernel, plan.D,
+             plan.B, plan.W, plan.NST, plan.append, plan.G, plan.gx, plan.gy, plan.gz, plan.W * 32, plan.smem);
+  else
+    snprintf(buf, buf_bytes, "vb200::%s<%d,%d,%d,%d,%d> grid=(%u,%u,%u) block=%d smem=%d", plan.kernel, plan.D,
+             plan.B, plan.W, plan.NST, plan.append, plan.gx, plan.gy, plan.gz, plan.W * 32, plan.smem);
+  return VB200_OK;
+}
+
+#ifdef VB200_EXPERIMENTS
+// Sweep knobs of the experiments build (tools/sweep.py); process-global on purpose, never in the shipped library.
+extern "C" int32_t vb200_debug_set_tuning(int32_t force_num_splits, int32_t variant) {
   const int32_t prev = (g_tuning.force_splits << 8) | (g_tuning.variant & 0xff);
   g_tuning.force_splits = force_num_splits < 0 ? 0 : force_num_splits;
   g_tuning.variant = (variant < 0 || variant >= kNumVariants) ? 0 : variant;
   return prev;
 }
+#endif

@@ -21,8 +21,13 @@ from . import _native
 _ERR_NAMES = {-1: "CUDA error", -2: "Unsupported block size", -3: "Unsupported head size",
               -4: "invalid argument", -5: "unsupported"}
 
-# per-device split-KV scratch (zero-filled once; the kernel leaves it reusable)
-_workspaces: Dict[int, torch.Tensor] = {}
+# Split-KV scratch, one per (device, stream, capture): the C ABI keeps no state -- the workspace is the caller's
+# (include/vllmini_b200.h) -- and this binding is that caller.  Launches on one stream are ordered, so they may share
+# a workspace; launches on different streams (or in different captured graphs, which may later be replayed
+# concurrently) get their own.  Zero-filled once, the kernel leaves it reusable.  Buffers are never freed: a
+# captured CUDA graph or an in-flight launch may still hold the raw pointer of one that was outgrown.
+_workspaces: Dict[tuple, torch.Tensor] = {}
+_retired_workspaces: List[torch.Tensor] = []
 
 
 def _check(rc: int) -> None:
@@ -37,14 +42,20 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"vllmini_b200: {name} must be a CUDA tensor, got device {t.device}")
 
 
-def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+def _workspace(device: torch.device, stream: int, nbytes: int) -> Optional[torch.Tensor]:
+    """Scratch for a split-KV launch on `stream` (a cudaStream_t handle); None when the shape never splits."""
     if nbytes <= 0:
         return None
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    ws = _workspaces.get(idx)
+    # a graph under capture gets a workspace of its own (allocated from the graph's private pool, zero-filled by a
+    # captured memset node), so two captured graphs replayed concurrently never share one
+    key = (idx, int(stream), int(_native.load().vb200_stream_capture_id(stream)))
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired_workspaces.append(ws)
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[idx] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -111,7 +122,7 @@ def paged_attention_v1(
     stream = torch.cuda.current_stream(dev).cuda_stream
     ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
                                                             int(max_seq_len))
-    ws = _workspace(dev, ws_bytes)
+    ws = _workspace(dev, stream, ws_bytes)
     rc = lib.vb200_paged_attention_v1_f16(
         out.data_ptr(), query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
         block_tables.data_ptr(), seq_lens.data_ptr(),
@@ -203,17 +214,17 @@ def paged_attention_v1_append(
     dev = query.device
     dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     lib = _native.load()
+    stream = torch.cuda.current_stream(dev).cuda_stream
     ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
                                                             int(max_seq_len))
-    ws = _workspace(dev, ws_bytes)
+    ws = _workspace(dev, stream, ws_bytes)
     rc = lib.vb200_paged_attention_v1_append_f16(
         out.data_ptr(), query.data_ptr(), key.data_ptr(), value.data_ptr(), key_cache.data_ptr(),
         value_cache.data_ptr(), slot_mapping.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
         num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size),
         block_tables.size(1) if block_tables.dim() == 2 else 0, int(max_seq_len),
         query.stride(0), key.stride(0), value.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
-        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, dev_index,
-        torch.cuda.current_stream(dev).cuda_stream)
+        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, dev_index, stream)
     _check(rc)
 
 
@@ -247,7 +258,8 @@ def add_layernorm(a: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, beta: t
     dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     rc = _native.load().vb200_add_layernorm_f16(
         x_out.data_ptr(), ln_out.data_ptr(), a.data_ptr(), a_rows.data_ptr() if a_rows is not None else None,
-        a.stride(0), x.data_ptr(), x_rows.data_ptr() if x_rows is not None else None, x.stride(0),
+        a.shape[0], a.stride(0), x.data_ptr(), x_rows.data_ptr() if x_rows is not None else None, x.shape[0],
+        x.stride(0),
         gamma.data_ptr(), beta.data_ptr(), num_rows, hidden, float(eps), dev_index,
         torch.cuda.current_stream(dev).cuda_stream)
     _check(rc)
@@ -315,12 +327,36 @@ def paged_attention_v2(
     blocksparse_block_size: int = 1,
     blocksparse_head_sliding_step: int = 0,
 ) -> None:
-    """The reference's split-KV entry (attention_kernels.cu:966-990; 512-token partitions + a reduce
-    kernel, :564-669).  Same result as paged_attention_v1; the B200 kernel already splits long contexts
-    inside v1 (with its own fp32 workspace and an in-kernel merge), so v2 validates the caller's scratch
-    tensors -- exp_sums / max_logits [S, H, P], tmp_out [S, H, P, D], P = ceil(max_seq_len / 512) -- and
-    runs the v1 path; the scratch tensors are left untouched."""
+    """The reference's partitioned entry (attention_kernels.cu:966-990; launcher :844-931).  The context is cut
+    into the reference's fixed 512-token partitions; every partition that holds a token of its sequence leaves its
+    record -- max logit, sum of exp(logit - max), normalised partial output -- in the CALLER's scratch tensors
+    exp_sums / max_logits [S, H, P] (fp32) and tmp_out [S, H, P, D] (fp16), P = ceil(max_seq_len / 512), exactly
+    where the reference's partition kernel puts them (:349-357, :484-495), and a second launch reduces the records
+    into `out` (:564-669).  No hidden workspace is involved."""
+    _require_cuda(query, "query")
+    if query.dtype is not torch.float16:
+        raise RuntimeError(f"vllmini_b200: unsupported input type of kv cache: {query.dtype}")
+    if kv_cache_dtype != "auto":
+        raise RuntimeError(f"vllmini_b200: Unsupported data type of kv cache: {kv_cache_dtype}")
+    if alibi_slopes is not None:
+        raise RuntimeError("vllmini_b200: alibi_slopes is not supported (vllmini passes None, gpt2.py:105)")
+    if blocksparse_vert_stride > 1:
+        raise RuntimeError("vllmini_b200: block-sparse attention is not supported")
+    for t, name in ((out, "out"), (exp_sums, "exp_sums"), (max_logits, "max_logits"), (tmp_out, "tmp_out"),
+                    (key_cache, "key_cache"), (value_cache, "value_cache"), (block_tables, "block_tables"),
+                    (seq_lens, "seq_lens")):
+        _require_cuda(t, name)
+    if block_tables.dtype is not torch.int32:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {block_tables.dtype} (block_tables)")
+    if seq_lens.dtype is not torch.int32:
+        raise RuntimeError(f"vllmini_b200: expected scalar type Int but found {seq_lens.dtype} (seq_lens)")
+    if any(t.dtype is not torch.float16 for t in (out, tmp_out, key_cache, value_cache)):
+        raise RuntimeError("vllmini_b200: out, tmp_out, key_cache and value_cache must be float16")
+    if query.dim() != 3 or query.stride(2) != 1 or query.stride(1) != query.size(2):
+        raise RuntimeError("vllmini_b200: query must be [num_seqs, num_heads, head_size] with contiguous heads")
     S, H, D = query.shape
+    if int(max_seq_len) <= 0:
+        raise RuntimeError("vllmini_b200: max_seq_len must be positive")
     P = (int(max_seq_len) + 511) // 512
     if tuple(exp_sums.shape) != (S, H, P) or tuple(max_logits.shape) != (S, H, P):
         raise RuntimeError(f"vllmini_b200: exp_sums/max_logits must be [{S}, {H}, {P}]")
@@ -328,10 +364,20 @@ def paged_attention_v2(
         raise RuntimeError(f"vllmini_b200: tmp_out must be [{S}, {H}, {P}, {D}]")
     if exp_sums.dtype is not torch.float32 or max_logits.dtype is not torch.float32:
         raise RuntimeError("vllmini_b200: exp_sums and max_logits must be float32")
-    paged_attention_v1(out, query, key_cache, value_cache, num_kv_heads, scale, block_tables, seq_lens,
-                       block_size, max_seq_len, alibi_slopes, kv_cache_dtype, kv_scale, tp_rank,
-                       blocksparse_local_blocks, blocksparse_vert_stride, blocksparse_block_size,
-                       blocksparse_head_sliding_step)
+    if not (out.is_contiguous() and exp_sums.is_contiguous() and max_logits.is_contiguous() and tmp_out.is_contiguous()
+            and block_tables.is_contiguous() and seq_lens.is_contiguous()):
+        raise RuntimeError("vllmini_b200: out, the scratch tensors, block_tables and seq_lens must be contiguous")
+    if out.numel() != query.numel():
+        raise RuntimeError("vllmini_b200: out must have num_seqs*num_heads*head_size elements")
+    dev = query.device
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    rc = _native.load().vb200_paged_attention_v2_f16(
+        out.data_ptr(), exp_sums.data_ptr(), max_logits.data_ptr(), tmp_out.data_ptr(), query.data_ptr(),
+        key_cache.data_ptr(), value_cache.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
+        S, H, int(num_kv_heads), D, int(block_size), block_tables.size(1) if block_tables.dim() == 2 else 0,
+        int(max_seq_len), query.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale), dev_index,
+        torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc)
 
 
 def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping: torch.Tensor) -> None:
