@@ -242,19 +242,20 @@ def test_reference_stack_on_dropin_matches_reference_stack_on_reference_kernels(
         assert all(np.array_equal(a, b) for a, b in zip(ref["logits"], mixed["logits"]))
 
     # ---- paged_attention_v1 inside the real stack: SURVEY.md 8c tolerance, carried to the logits ----
-    # deeper layers see each other's fp16-rounding differences; caches stay close, logits within 3e-2
-    # (|logit| ~ 1; the attention outputs themselves differ by <= 2e-3 + 1e-2 |ref|)
+    # deeper layers see each other's fp16-rounding differences; caches stay close, logits within 1e-2
+    # (|logit| ~ 1; the attention outputs themselves differ by <= 2e-3 + 1e-2 |ref|; measured on B200: 3.9e-3 over
+    # 12 layers x 24 steps, 3.2e-3 over 4 layers x 70 steps)
     assert (ref["kc"].float() - new["kc"].float()).abs().max().item() < 5e-2
     assert (ref["vc"].float() - new["vc"].float()).abs().max().item() < 5e-2
     worst = 0.0
     for i, (a, b) in enumerate(zip(ref["logits"], new["logits"])):
         d = float(np.abs(a - b).max())
         worst = max(worst, d)
-        assert d < 3e-2, f"forward {i}: logits differ by {d:.4f}"
+        assert d < 1e-2, f"forward {i}: logits differ by {d:.4f}"
         if i < len(prompts) and deterministic:
             assert np.array_equal(a, b), "prefill logits must be identical (no paged kernel involved)"
         top2 = np.sort(a)[-2:]
-        if top2[1] - top2[0] > 6e-2:
+        if top2[1] - top2[0] > 2e-2:
             assert int(a.argmax()) == int(b.argmax()), f"forward {i}: greedy token differs"
     print(f"[reference host] {layers} layers x {steps} steps: max |logit(new) - logit(ref)| = {worst:.2e}; "
           f"cuBLAS run-to-run deterministic: {deterministic}")

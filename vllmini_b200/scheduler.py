@@ -38,8 +38,12 @@ class BatchedScheduler:
         if sampling not in ("greedy", "top_k"):
             raise ValueError("sampling must be 'greedy' or 'top_k'")
         self.model, self.kv = model, kv
-        # a sequence can never outgrow its block-table row
+        # a sequence can never outgrow its block-table row, nor the model's position table (wpe has n_positions rows;
+        # the fused embedding launch traps on a position beyond it instead of reading out of bounds)
         self.max_length = min(int(max_length), kv.max_blocks_per_seq * kv.block_size)
+        n_positions = getattr(getattr(model, "shape", None), "n_positions", None)
+        if n_positions is not None:
+            self.max_length = min(self.max_length, int(n_positions))
         self.eos_token_id = eos_token_id
         self.sampling, self.top_k, self.temperature = sampling, int(top_k), float(temperature)
         self.use_graph = use_graph
@@ -84,15 +88,22 @@ class BatchedScheduler:
         return seq_id
 
     def _blocks_needed(self, prompt_len: int) -> int:
-        B = self.kv.block_size
-        return ((prompt_len + B - 1) // B) * self.kv.num_layers
+        """Blocks an admission must find free: the prompt's, the block its FIRST decoded token may open (prompt
+        length a multiple of the block size) and the blocks the rows already running will open in the coming step
+        -- otherwise the step right after a prefill could run out of blocks and the eviction rule (newest sequence
+        goes, scheduler.py:117-131) would throw away the prompt that was just prefilled."""
+        kv = self.kv
+        B = kv.block_size
+        own = ((prompt_len + 1 + B - 1) // B) * kv.num_layers
+        growing = int(((kv.h_lens[kv.active] % B) == 0).sum()) * kv.num_layers
+        return own + growing
 
     def _admit(self) -> None:
         kv = self.kv
         while self.pending:
             seq_id, ids = self.pending[0]
-            if len(ids) > kv.max_blocks_per_seq * kv.block_size:
-                self.pending.popleft()
+            if len(ids) > min(kv.max_blocks_per_seq * kv.block_size, self.max_length):
+                self.pending.popleft()           # can never run: longer than a table row / the position table
                 self._retire(seq_id, "evicted")
                 continue
             try:

@@ -78,6 +78,30 @@ def broadcast_state_dict(state: Dict[str, torch.Tensor], src: int = 0, bucket_by
             bucket, size = ([t], t.numel() * t.element_size()) if t is not None else ([], 0)
 
 
+def replicas_agree(state: Dict[str, torch.Tensor]) -> bool:
+    """True when every rank holds the same weights: per-tensor fp64 checksums (sum and sum of squares) are
+    all_reduced with MAX and MIN and must coincide.  One small collective, outside any timed region; trivially True
+    without a process group."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return True
+    names = sorted(state)
+    dev = state[names[0]].device
+    sums = torch.stack([torch.stack([state[n].double().sum(), state[n].double().square().sum()]) for n in names]).reshape(-1)
+    sums = torch.nan_to_num(sums).to(dev)
+    hi, lo = sums.clone(), sums.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(torch.equal(hi, lo))
+
+
+def reduce_sum(values: Sequence[float], device: torch.device) -> List[float]:
+    """Sum over ranks of a few host scalars (token counts)."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()]
+
+
 def reduce_max(values: Sequence[float], device: torch.device) -> List[float]:
     """Max over ranks of a few host scalars (timings): the job is as slow as its slowest rank."""
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
