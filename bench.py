@@ -21,6 +21,12 @@ binding.  tokens/s = sequences advanced per step / step time.
             step % 12) INSIDE the timed region, against the measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline  the reference's CPU-runnable attention (torch eager, oracle/eager_attention.py)
             on the host cores over a bounded sample of the same tensors, rank 0, N=1 only
+  ref_kernel the reference's OWN CUDA kernel (oracle/_ref, rebuilt for sm_100) on the same tensors as the new
+            kernel, same CUDA-graph timing: the number that measures the kernel work
+  configs   the same pair of timings for BASELINE configs[1], [2] and the nine configs[3] cells (N=1 only)
+  continuous  BASELINE configs[2] / [4] as written: mixed-length requests, request-sharded over the ranks with
+            sharding.balanced_shards_by_length, each rank running the continuous-batching scheduler with
+            admissions inside the window; whole GPT-2 small model; tokens/s = all ranks' tokens / max time
 
 `--impl reference` times that CPU path alone (all host threads) and prints the same line shape.
 """
@@ -71,12 +77,18 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram bytes per attention launch from the committed ncu --set full capture, or None."""
+    """(dram bytes per attention launch, where the figure comes from): read from the committed ncu --set full
+    capture -- a static record refreshed by tools/gpu_round.sh, NOT measured in this run (ncu cannot run inside a
+    timed bench) -- or (None, reason)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["pa_v1_dram_bytes_per_launch"])
-    except Exception:
-        return None
+        with open(path) as f:
+            d = json.load(f)
+        src = "static: profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum"
+        src += f", kernel {d.get('kernel', '?')}, captured at {d.get('commit', d.get('source', '?'))})"
+        return float(d["pa_v1_dram_bytes_per_launch"]), src
+    except Exception as e:
+        return None, f"unavailable: {e!r}"
 
 
 # ---- clock sampling during the timed region (NVML) ------------------------------------------
@@ -130,78 +142,96 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ---- CPU baseline: the reference's CPU-runnable attention on a bounded sample ---------------------
-def cpu_attention_sample(target_seconds=12.0, threads=None, seed=0):
-    """Times oracle/eager_attention.py (port of vllmini/model/gpt2.py:71-78 over block-table
-    gathered K/V) on `n` sequences x 1 layer of the bench workload and scales to tokens/s of the
-    12-layer step:  tokens/s = n / (12 * t_layer(n))."""
-    import torch
-    from oracle import eager_attention
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(seed)
+# ---- CPU baseline: the reference's CPU-runnable path on a bounded sample ------------------------------
+CPU_SAMPLE_SEQS = 16
 
-    def make(n):
+
+def bench_config(world):
+    """`config` of the JSON line -- the same dict for both arms (the reference arm runs on this arm's config)."""
+    return {"workload": WORKLOAD, "global_batch": world * S, "seq_len": CTX,
+            "parallelism": f"request-sharded x{world} (no data-path collective)",
+            "kv_pool_gb_per_gpu": round(2 * LAYERS * S * (CTX // B) * H * D * B * 2 / 1e9, 2),
+            "l2_policy": "inputs larger than L2: each layer reads 805 MB of distinct KV blocks, "
+                         "9.66 GB per step, no flush needed",
+            "timing": "CUDA events on the launch stream, max over ranks"}
+
+
+class CpuHotPathSample:
+    """One layer of the bench step for `n` of the 256 sequences, on the host: the new token's K/V rows are
+    scattered into the paged caches (oracle.paged_oracle.reshape_and_cache, the numpy restatement of
+    cache_kernels.cu:152-207) and the reference's own CPU-runnable attention (torch eager fp32
+    softmax(QK^T)V over block-table-gathered K/V, oracle/eager_attention.py = vllmini/model/gpt2.py:71-78) runs
+    over the 1024 cached tokens.  tokens/s of the 12-layer step = n / (12 * t_layer)."""
+
+    def __init__(self, n=CPU_SAMPLE_SEQS, seed=0, threads=None):
+        import numpy as np
+        import torch
+        self.torch, self.np, self.n = torch, np, n
+        self.threads = threads or os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        g = torch.Generator().manual_seed(seed)
         nblk = CTX // B
         nb = n * nblk
-        kc = torch.randn(nb, H, D // 8, B, 8, generator=g).to(torch.float16)
-        vc = torch.randn(nb, H, D, B, generator=g).to(torch.float16)
-        q = torch.randn(n, H, D, generator=g).to(torch.float16)
-        bt = torch.randperm(nb, generator=g).to(torch.int32).view(n, nblk)
-        sl = torch.full((n,), CTX, dtype=torch.int32)
-        return q, kc, vc, bt, sl
+        self.kc = torch.randn(nb, H, D // 8, B, 8, generator=g).to(torch.float16)
+        self.vc = torch.randn(nb, H, D, B, generator=g).to(torch.float16)
+        self.qkv = torch.randn(n, 3 * H * D, generator=g).to(torch.float16)
+        self.bt = torch.randperm(nb, generator=g).to(torch.int32).view(n, nblk)
+        self.sl = torch.full((n,), CTX, dtype=torch.int32)
+        self.slots = (self.bt[:, -1].to(torch.int64) * B + (CTX - 1) % B).numpy()
 
-    def run(n, reps):
-        q, kc, vc, bt, sl = make(n)
-        eager_attention.paged_attention_eager_cpu(q, kc, vc, bt, sl, D ** -0.5)  # warm
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            eager_attention.paged_attention_eager_cpu(q, kc, vc, bt, sl, D ** -0.5)
-        return (time.perf_counter() - t0) / reps
+    def step(self):
+        from oracle import eager_attention
+        from oracle import paged_oracle as po
+        q = self.qkv[:, : H * D].view(self.n, H, D)
+        k = self.qkv[:, H * D: 2 * H * D].view(self.n, H, D)
+        v = self.qkv[:, 2 * H * D:].view(self.n, H, D)
+        po.reshape_and_cache(k.numpy(), v.numpy(), self.kc.numpy(), self.vc.numpy(), self.slots)
+        return eager_attention.paged_attention_eager_cpu(q, self.kc, self.vc, self.bt, self.sl, D ** -0.5)
 
-    n = 16
-    t = run(n, 1)
+    def sample_text(self, reps):
+        return (f"{self.n} of 256 sequences x 1 of 12 layers (ctx {CTX}), {reps} reps: reshape_and_cache (numpy "
+                f"restatement of cache_kernels.cu:152-207) + torch-eager fp32 gather+softmax(QK^T)V (port of "
+                f"vllmini/model/gpt2.py:71-78), {self.threads} threads; scaled: tokens/s = n / (12 * t_layer)")
+
+
+def cpu_attention_sample(target_seconds=12.0, threads=None, seed=0):
+    import time as _t
+    cs = CpuHotPathSample(seed=seed, threads=threads)
+    cs.step()  # warm
+    t0 = _t.perf_counter()
+    cs.step()
+    t = _t.perf_counter() - t0
     reps = max(1, min(50, int(target_seconds / max(t, 1e-4))))
-    t = run(n, reps)
-    return {"value": n / (LAYERS * t), "unit": "tokens/s", "cores": threads, "kind": "port",
-            "sample": f"{n} of 256 sequences x 1 of 12 layers (ctx {CTX}), {reps} reps, torch-eager fp32 "
-                      f"gather+softmax(QK^T)V (port of vllmini/model/gpt2.py:71-78); scaled: n/(12*t_layer)",
-            "seconds_per_layer_sample": t}
+    t0 = _t.perf_counter()
+    for _ in range(reps):
+        cs.step()
+    t = (_t.perf_counter() - t0) / reps
+    return {"value": cs.n / (LAYERS * t), "unit": "tokens/s", "cores": cs.threads, "kind": "port",
+            "sample": cs.sample_text(reps), "seconds_per_layer_sample": t}
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the reference's CPU implementation of the path, all host threads."""
+    """`--impl reference`: the reference's CPU implementation of the path, all host threads, on this bench's own
+    config; each step is the bounded sample CpuHotPathSample describes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    from oracle import eager_attention
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    n = 16
-    nblk = CTX // B
-    kc = torch.randn(n * nblk, H, D // 8, B, 8, generator=g).to(torch.float16)
-    vc = torch.randn(n * nblk, H, D, B, generator=g).to(torch.float16)
-    q = torch.randn(n, H, D, generator=g).to(torch.float16)
-    bt = torch.randperm(n * nblk, generator=g).to(torch.int32).view(n, nblk)
-    sl = torch.full((n,), CTX, dtype=torch.int32)
+    cs = CpuHotPathSample()
     for _ in range(max(args.warmup, 1)):
-        eager_attention.paged_attention_eager_cpu(q, kc, vc, bt, sl, D ** -0.5)
+        cs.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eager_attention.paged_attention_eager_cpu(q, kc, vc, bt, sl, D ** -0.5)
+        cs.step()
     t = (time.perf_counter() - t0) / args.steps
-    value = n / (LAYERS * t)
-    sample = (f"each step = {n} of 256 sequences x 1 of 12 layers (ctx {CTX}); tokens/s = n/(12*t_step); "
-              "torch-eager fp32 attention over block-table-gathered K/V (oracle port of "
-              "vllmini/model/gpt2.py:71-78; the reference has no other CPU path and its CUDA extension "
-              "is not a CPU implementation)")
+    value = cs.n / (LAYERS * t)
+    sample = "each step = " + cs.sample_text(1) + ("; the reference has no other CPU path and its CUDA extension is "
+                                                    "not a CPU implementation (timed as `ref_kernel` by the GPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": bench_config(max(world, 1)),
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cs.threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -347,26 +377,202 @@ class HostDrivenStep:
             cur.wait_stream(self.s_out)
 
 
-def run_full_model(args, dev, world, rank):
-    """Whole GPT-2 small decode step (cuBLAS GEMMs + GELU via torch; the hot ops, residual-add+LayerNorm
-    and argmax via the library) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
-    driver of SURVEY.md 8f rank 1), CUDA-graph replayed.  Reported as context next to the hot-path
-    `value`; at N>1 rank 0's weights are broadcast over NCCL first (the path's only collective)."""
+# ---- the reference's own CUDA kernel next to the new one (SURVEY.md 8d "reference-on-GPU row") ------------------
+def load_reference_kernels():
+    """oracle/_ref/paged_attention_cuda*.so: the reference's three source files compiled unmodified for sm_100 by
+    oracle/build_ref.py -- a GPU comparator (checker-side artefact, never on the product path).  None if absent."""
+    import glob
+    import importlib.util
+    hits = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "paged_attention_cuda*.so")))
+    if not hits:
+        return None
+    spec = importlib.util.spec_from_file_location("paged_attention_cuda", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# BASELINE.json configs[1..3] at full size + the metric shape: (S, H, D, B, ctx); ctx < 0 => seq_lens ~ U[128, |ctx|]
+KERNEL_CELLS = [
+    ("metric 256x1024 12x64 blk16", (256, 12, 64, 16, 1024)),
+    ("configs[1] 64x512 12x64 blk16", (64, 12, 64, 16, 512)),
+    ("configs[2] 256xU[128,2048] 12x64 blk16", (256, 12, 64, 16, -2048)),
+] + [(f"configs[3] 256x{ctx // 1024}k 20x64 blk{blk}", (256, 20, 64, blk, ctx))
+     for ctx in (1024, 4096, 8192) for blk in (8, 16, 32)]
+
+
+def time_attention_cell(torch, dev, impls, shape, iters=20, replays=5):
+    """Median us per paged_attention_v1 launch for every binding in `impls` ({name: module}) on the SAME tensors:
+    `iters` launches over rotating KV pools (>= 4 pools or >= 1 GiB in total, random block tables: no L2 reuse)
+    captured in one CUDA graph per binding (no host launch overhead) and replayed `replays` times."""
+    S_, H_, D_, B_, ctx = shape
+    mixed, ctx = ctx < 0, abs(ctx)
+    g = torch.Generator(device=dev).manual_seed(7)
+    kv_bytes = 2 * S_ * ctx * H_ * D_ * 2
+    npools = 2 if kv_bytes >= (1 << 30) else max(2, min(6, (1 << 30) // kv_bytes + 1))
+    nblk = (ctx + B_ - 1) // B_
+    pools = []
+    for _ in range(npools):
+        lens = (torch.randint(128, ctx + 1, (S_,), generator=g, device=dev, dtype=torch.int32) if mixed
+                else torch.full((S_,), ctx, dtype=torch.int32, device=dev))
+        NB = S_ * nblk
+        kc = torch.empty(NB, H_, D_ // 8, B_, 8, device=dev, dtype=torch.float16).normal_(generator=g)
+        vc = torch.empty(NB, H_, D_, B_, device=dev, dtype=torch.float16).normal_(generator=g)
+        q = torch.randn(S_, H_, D_, generator=g, device=dev, dtype=torch.float16)
+        bt = torch.randperm(NB, generator=g, device=dev).to(torch.int32).view(S_, nblk).contiguous()
+        pools.append((q, kc, vc, bt, lens, torch.empty_like(q)))
+    ab = sum(2 * int(p[4].sum()) * H_ * D_ * 2 + 2 * S_ * H_ * D_ * 2 + int(((p[4] + B_ - 1) // B_).sum()) * 4 + S_ * 4
+             for p in pools) / npools
+    res = {"algorithmic_bytes": ab}
+    outs = {}
+    for name, mod in impls.items():
+        def call(i, mod=mod):
+            q, kc, vc, bt, sl, out = pools[i % npools]
+            mod.paged_attention_v1(out, q, kc, vc, H_, D_ ** -0.5, bt, sl, B_, ctx, None, "auto", 1.0, 0, 0, 1, 1, 0)
+        for i in range(npools + 1):
+            call(i)
+        torch.cuda.synchronize()
+        outs[name] = pools[0][5].clone()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(iters):
+                call(i)
+        gr.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(replays):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / iters)
+        del gr
+        us = sorted(ts)[len(ts) // 2]
+        res[name + "_us"] = us
+        res[name + "_gbps"] = ab / us / 1e3
+    if "new" in outs and "ref" in outs:      # the two kernels really computed the same thing on these tensors
+        res["max_abs_diff_new_vs_ref"] = float((outs["new"].float() - outs["ref"].float()).abs().max())
+    del pools, outs
+    torch.cuda.empty_cache()
+    return res
+
+
+def kernel_comparison(torch, dev, ops, peak, cells):
+    """{cell: {new_us, ref_us, speedup, new_gbps, ref_gbps, frac_of_8TBps, frac_of_measured_peak}}."""
+    ref = load_reference_kernels()
+    impls = {"new": ops} if ref is None else {"new": ops, "ref": ref}
+    out = {}
+    for name, shape in cells:
+        r = time_attention_cell(torch, dev, impls, shape)
+        rec = {"new_us": round(r["new_us"], 2), "new_gbps": round(r["new_gbps"], 1),
+               "frac_of_8TBps": round(r["new_gbps"] / 8000.0, 4), "frac_of_measured_peak": round(r["new_gbps"] / peak, 4),
+               "algorithmic_bytes": r["algorithmic_bytes"]}
+        if "ref_us" in r:
+            rec.update({"ref_us": round(r["ref_us"], 2), "ref_gbps": round(r["ref_gbps"], 1),
+                        "speedup": round(r["ref_us"] / r["new_us"], 3),
+                        "max_abs_diff_new_vs_ref": r["max_abs_diff_new_vs_ref"]})
+        out[name] = rec
+    return out, ref is not None
+
+
+# ---- BASELINE configs[2] / configs[4] as written: continuous batching, request-sharded ------------------------------
+def run_continuous(args, dev, world, rank, model, shape):
+    """256 x N mixed-length requests (+12.5 % oversubscription so that admissions happen inside the window), prompt
+    lengths ~ U[128, 2040] (seed 0, the same global list on every rank), dealt to the ranks by
+    sharding.balanced_shards_by_length (longest-first: equal KV bytes per rank); every rank runs its own
+    BatchedScheduler (256 rows, max_length 2048, greedy, CUDA-graph decode step, graphed bucket-padded prefill) over
+    its private KV pool.  Timed window: `steps` scheduler steps after a short warm-up; tokens/s = tokens generated by
+    all ranks / the slowest rank's time.  No data-path collective."""
+    import numpy as np
     import torch
     from vllmini_b200 import sharding
-    from vllmini_b200.decode import BatchedKVState, GPT2Decoder, GPT2Shape, synthetic_gpt2_state_dict
+    from vllmini_b200.decode import BatchedKVState
+    from vllmini_b200.scheduler import BatchedScheduler
 
+    MAXLEN = shape.n_positions
+    per_rank = S + S // 8
+    rng = np.random.default_rng(0)
+    lens = rng.integers(128, 2041, size=world * per_rank)
+    shards = sharding.balanced_shards_by_length(lens.tolist(), world)
+    mine = shards[rank]
+    loads = [int(sum(int(lens[i]) for i in sh)) for sh in shards]
+    MB = MAXLEN // B
+    kv = BatchedKVState(LAYERS * S * MB, LAYERS, H, D, B, S, MB, dev)
+    sch = BatchedScheduler(model, kv, max_length=MAXLEN, use_graph=True)
+    t0 = time.perf_counter()
+    prng = np.random.default_rng(1000 + rank)
+    for i in mine:
+        sch.add_sequence(prng.integers(0, shape.vocab_size, size=int(lens[i])).tolist())
+    torch.cuda.synchronize()
+    t_prefill = time.perf_counter() - t0
+    for _ in range(5):
+        sch.step()
+    torch.cuda.synchronize()
+    steps = min(max(args.steps, 20), 100)
+    if world > 1:
+        torch.distributed.barrier()
+    tok0, fin0 = sch.tokens_generated, len(sch.finished)
+    ctx = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.append(float(np.mean([sch.sequence_lengths[s_] for s_ in sch.rows if s_ is not None] or [0])))
+        sch.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = sharding.reduce_max([e0.elapsed_time(e1)], dev)[0]
+    tokens, finished, pending = sharding.reduce_sum([sch.tokens_generated - tok0, len(sch.finished) - fin0,
+                                                     len(sch.pending)], dev)
+    rec = {"value": tokens / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms / steps, "steps": steps,
+           "requests": int(world * per_rank), "requests_this_rank": len(mine),
+           "kv_tokens_per_rank_min_max": [min(loads), max(loads)],
+           "mean_ctx_rank0": float(np.mean(ctx)), "finished_in_window": int(finished), "still_pending": int(pending),
+           "prefill_s_rank0": t_prefill,
+           "how": "BASELINE configs[2] (N=1) / configs[4] (N=8): whole GPT-2 small, prompts U[128,2040], max_length 2048, "
+                  "request-sharded by sharding.balanced_shards_by_length, vllmini_b200.scheduler.BatchedScheduler per "
+                  "rank with admissions inside the window; tokens of all ranks / max-over-ranks CUDA-event time"}
+    del sch, kv
+    torch.cuda.empty_cache()
+    return rec
+
+
+def build_model(dev, world, rank):
+    """GPT-2 small (n_positions raised to 2048) with seeded synthetic weights.  At N>1 every rank starts from
+    DIFFERENT weights, rank 0's are broadcast over NCCL (the path's only collective) and one all_reduce of
+    per-tensor checksums proves the replicas agree afterwards -- a broken broadcast fails the run."""
+    import torch
+    from vllmini_b200 import sharding
+    from vllmini_b200.decode import GPT2Decoder, GPT2Shape, synthetic_gpt2_state_dict
     shape = GPT2Shape(n_positions=2048)                    # ctx > 1024 needs n_positions raised (SURVEY.md section 0)
     model = GPT2Decoder(shape, dev)
-    t0 = time.perf_counter()
     model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=0 if rank == 0 else 1000 + rank))
-    t_bcast = None
+    info = {"weight_broadcast_s": None, "replicas_agree": None}
     if world > 1:
+        differed = not sharding.replicas_agree(model.state_dict())     # sanity: the ranks really started apart
         torch.cuda.synchronize()
         tb = time.perf_counter()
         model.broadcast_weights(src=0)
         torch.cuda.synchronize()
-        t_bcast = time.perf_counter() - tb
+        info["weight_broadcast_s"] = time.perf_counter() - tb
+        info["replicas_agree"] = sharding.replicas_agree(model.state_dict())
+        info["replicas_differed_before_broadcast"] = differed
+        if not info["replicas_agree"]:
+            raise RuntimeError("weight replicas differ after the NCCL broadcast")
+    return model, shape, info
+
+
+def run_full_model(args, dev, world, rank, model, shape, info):
+    """Whole GPT-2 small decode step (cuBLAS GEMMs + GELU via torch; the hot ops, residual-add+LayerNorm
+    and argmax via the library) for 256 sequences at ctx ~1024 per GPU, driven by vllmini_b200.decode (the batched
+    driver of SURVEY.md 8f rank 1), CUDA-graph replayed.  This is the literal "decode tokens/s, GPT-2" of the
+    metric; `value` is the hot path alone."""
+    import torch
+    from vllmini_b200 import sharding
+    from vllmini_b200.decode import BatchedKVState
+
+    t0 = time.perf_counter()
+    t_bcast = info["weight_broadcast_s"]
     MB = 72                                                 # capacity 1152 tokens per sequence
     kv = BatchedKVState(LAYERS * S * MB, LAYERS, H, D, B, S, MB, dev)
     g = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -416,7 +622,23 @@ def run_full_model(args, dev, world, rank):
                    "graph: per layer 4 cuBLAS GEMMs + GELU (torch), the fused append+attention launch and two fused "
                    "residual-add+LayerNorm launches (own kernels); lm_head on the 64-row-padded tied embedding; "
                    "own row-argmax",
-            "weight_broadcast_s": t_bcast, "setup_s": time.perf_counter() - t0}
+            "weight_broadcast_s": t_bcast, "replicas_agree_after_broadcast": info["replicas_agree"],
+            "setup_s": time.perf_counter() - t0}
+
+
+def pin_rank_to_cores(world, local_rank):
+    """N ranks + their NVML sampler and copy-enqueue threads share one host: give every rank a disjoint slice of the
+    cores this process may run on, so that the ranks do not migrate over each other (the e2e leg is host-paced)."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(allowed) < 2 * world:
+            return f"unpinned ({len(allowed)} cores visible)"
+        per = len(allowed) // world
+        mine = allowed[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return f"{per} cores per rank, disjoint (rank-local cores {mine[0]}-{mine[-1]} of {len(allowed)})"
+    except Exception as e:   # not Linux / no permission: run unpinned
+        return f"unpinned ({e!r})"
 
 
 def run_gpu_arm(args):
@@ -438,6 +660,7 @@ def run_gpu_arm(args):
                            "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = pin_rank_to_cores(world, local_rank)
     # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever
     # a library prints (NCCL writes its version banner to stdout) cannot end up next to the result
     result_out = os.fdopen(os.dup(1), "w")
@@ -543,65 +766,82 @@ def run_gpu_arm(args):
         barrier()
         return dt
 
-    # the step is issued two ways through the same binding -- enqueued call by call, and replayed from a CUDA graph
-    # captured over the same calls and copies; which one is faster depends on the box's host (enqueue cost vs graph
-    # launch cost), so both are timed and the faster one is the e2e figure
+    # The step is issued two ways through the same binding: replayed from a CUDA graph captured over the same calls
+    # and copies -- THE e2e figure, always -- and enqueued call by call (context: depends on the box's host).
     e2e_eager_s = time_e2e(lambda: hd.step(ops))
-    e2e_graph_s = float("inf")
-    if not args.e2e_eager:
-        try:
-            torch.cuda.synchronize()
-            hd.capture(ops)
-            for _ in range(warm):
-                hd.step_graph()
-            e2e_graph_s = time_e2e(hd.step_graph)
-        except Exception as e:
-            print(f"[bench] e2e graph capture failed, eager enqueue only: {e!r}", file=sys.stderr)
+    e2e_graph_s = None
+    torch.cuda.synchronize()
+    hd.capture(ops)
+    for _ in range(warm):
+        hd.step_graph()
+    e2e_graph_s = time_e2e(hd.step_graph)
 
     from vllmini_b200 import sharding
     ms_total, e2e_eager_s, e2e_graph_s, fused_ms = sharding.reduce_max([ms_total, e2e_eager_s, e2e_graph_s, fused_ms],
                                                                          dev)   # slowest rank sets the pace
-    e2e_s, e2e_mode = (e2e_eager_s, "eager enqueue") if e2e_eager_s <= e2e_graph_s else (e2e_graph_s, "CUDA-graph replay")
+    e2e_s = e2e_graph_s
 
-    full_model = None
     h2d_bytes, d2h_bytes = hd.h2d, hd.d2h
-    if not args.no_full_model:
-        del hd
-        hp.key_cache = hp.value_cache = None
-        torch.cuda.empty_cache()
+    del hd
+    hp.key_cache = hp.value_cache = None
+    del hp
+    torch.cuda.empty_cache()
+
+    # ---- the reference's own kernel and the other BASELINE configs (N=1: one GPU's worth of comparison) ----
+    peak, peak_src = measured_peak()
+    cells, have_ref = None, False
+    if world == 1 and not args.no_configs:
         try:
-            full_model = run_full_model(args, dev, world, rank)
+            cells, have_ref = kernel_comparison(torch, dev, ops, peak, KERNEL_CELLS)
         except Exception as e:
-            full_model = {"value": None, "error": repr(e)}
+            cells = {"error": repr(e)}
+
+    # ---- whole model: uniform-context decode step, then continuous batching (configs[2] / configs[4]) ----
+    full_model = continuous = None
+    if not args.no_full_model:
+        try:
+            model, shape, info = build_model(dev, world, rank)
+            full_model = run_full_model(args, dev, world, rank, model, shape, info)
+            torch.cuda.empty_cache()
+            if not args.no_continuous:
+                continuous = run_continuous(args, dev, world, rank, model, shape)
+        except Exception as e:
+            if full_model is None:
+                full_model = {"value": None, "error": repr(e)}
+            else:
+                continuous = {"value": None, "error": repr(e)}
 
     if rank == 0:
         ms_step = ms_total / args.steps
         value = world * S / (ms_step * 1e-3)
         e2e_value = world * S / (e2e_s / args.steps)
-        peak, peak_src = measured_peak()
         ab = algorithmic_bytes_attention(S, CTX)
         attn_mean_us = sum(attn_us) / len(attn_us)
         achieved = ab / (attn_mean_us * 1e-6) / 1e9
+        traffic, traffic_src = recorded_traffic()
+        config = bench_config(world)
+        config["cpu_affinity"] = affinity
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * S, "seq_len": CTX,
-                       "parallelism": f"request-sharded x{world} (no data-path collective)",
-                       "kv_pool_gb_per_gpu": round(2 * LAYERS * S * (CTX // B) * H * D * B * 2 / 1e9, 2),
-                       "l2_policy": "inputs larger than L2: each layer reads 805 MB of distinct KV blocks, "
-                                    "9.66 GB per step, no flush needed",
-                       "timing": "CUDA events on the launch stream, max over ranks"},
+            # `value` times the 24 hot-path launches of a step, not a whole GPT-2 decode step: anyone quoting
+            # "GPT-2 decode tokens/s" must quote decode_tokens_per_s_full_model
+            "hot_path_only": True,
+            "decode_tokens_per_s_full_model": (full_model or {}).get("value"),
+            "config": config,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "ms_per_step_eager_enqueue": e2e_eager_s / args.steps * 1e3,
-                    "ms_per_step_graph_replay": (e2e_graph_s / args.steps * 1e3) if e2e_graph_s != float("inf") else None,
-                    "how": "per layer one packed pinned buffer (q/k/v + slot mapping + block table) -> device, "
-                           "2 launches through the binding, attention output -> pinned host; copies pipelined "
-                           "against compute on 3 streams; host sync every step; step issued by " + e2e_mode},
+                    "how": "CUDA-graph replay of the step (always; the call-by-call enqueue of the same step is "
+                           "ms_per_step_eager_enqueue, context only): per layer one packed pinned buffer (q/k/v + slot "
+                           "mapping + block table) -> device, 2 launches through the binding, attention output -> pinned "
+                           "host; copies pipelined against compute on 3 streams; host sync and a read of the output every "
+                           "step.  The pinned input buffers keep their contents between steps (the host does not "
+                           "re-generate inputs; every step still copies all of them)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "vb200::pa_v1_kernel<64,16,4,2>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": _native.plan(S, H, H, D, B, CTX), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "frac_of_nominal_8TBps": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": ab, "mean_launch_us": attn_mean_us,
@@ -613,8 +853,21 @@ def run_gpu_arm(args):
                          "attention_share_of_step_kernels": attn_mean_us / (attn_mean_us + sum(resh_us) / len(resh_us)),
                          "probed_layer_us_x12_over_step": (attn_mean_us + sum(resh_us) / len(resh_us)) * LAYERS
                                                           / (ms_step * 1e3),
-                         "traffic": recorded_traffic()},
+                         "traffic": traffic, "traffic_source": traffic_src},
         }
+        if cells is not None:
+            m = cells.get(KERNEL_CELLS[0][0], {})
+            if "ref_us" in m:
+                line["ref_kernel"] = {
+                    "speedup": m["speedup"], "new_us": m["new_us"], "ref_us": m["ref_us"], "new_gbps": m["new_gbps"],
+                    "ref_gbps": m["ref_gbps"],
+                    "how": "the reference's own paged_attention_v1 kernel (attention_kernels.cu:499-527, its three "
+                           "source files compiled unmodified for sm_100 by oracle/build_ref.py) and the new kernel on "
+                           "identical tensors at the metric shape: 20 launches over rotating KV pools per CUDA graph, "
+                           "median of 5 replays, us per launch"}
+            elif not have_ref:
+                line["ref_kernel"] = {"unavailable": "oracle/_ref/paged_attention_cuda*.so not present"}
+            line["configs"] = cells
         if fused_ms > 0:
             line["fused_step"] = {"value": world * S / (fused_ms / args.steps * 1e-3), "unit": "tokens/s",
                                   "ms_per_step": fused_ms / args.steps,
@@ -627,6 +880,8 @@ def run_gpu_arm(args):
                                          "(rank-local, not max-reduced)"}
         if full_model is not None:
             line["full_model"] = full_model
+        if continuous is not None:
+            line["continuous"] = continuous
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_attention_sample()
@@ -648,9 +903,9 @@ def main():
     ap.add_argument("--impl", default="vllmini_b200", choices=["vllmini_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-model", action="store_true", help="skip the whole-GPT-2 decode context row")
-    ap.add_argument("--e2e-eager", action="store_true",
-                    help="e2e: time only the eager enqueue (default: also the CUDA-graph replay of the same step, "
-                         "the faster of the two is reported)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the reference-kernel comparison over BASELINE configs[1-3] (N=1 only anyway)")
+    ap.add_argument("--no-continuous", action="store_true", help="skip the continuous-batching record")
     ap.add_argument("--no-extras", action="store_true", help="skip the fused_step / graph_step context rows")
     args = ap.parse_args()
     if args.impl == "reference":

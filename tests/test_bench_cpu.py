@@ -24,6 +24,22 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the reference arm runs on the GPU arm's own config: the same dict, and its step includes both ops of the path
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(1)
+    assert "reshape_and_cache" in cb["sample"] and "softmax" in cb["sample"]
+
+
+def test_kernel_cells_cover_baseline_configs_1_to_3():
+    sys.path.insert(0, ROOT)
+    import bench
+    names = [n for n, _ in bench.KERNEL_CELLS]
+    assert len(names) == 3 + 9 and names[0].startswith("metric")
+    assert sum(n.startswith("configs[3]") for n in names) == 9
+    shapes = dict(bench.KERNEL_CELLS)
+    assert shapes["configs[1] 64x512 12x64 blk16"] == (64, 12, 64, 16, 512)
+    assert shapes["configs[3] 256x8k 20x64 blk8"] == (256, 20, 64, 8, 8192)
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():

@@ -131,3 +131,37 @@ def test_top_k_sampling_is_seeded_and_stays_inside_the_top_k():
         assert all(10 <= t < 15 for t in sch.sequences[i][1:] + sch.sequences[j][2:])
     assert outs[0] == outs[1]                   # same seed, same draws
     assert len(set(outs[0][0][1:])) > 1         # and it does sample
+
+
+def test_admission_reserves_the_first_decode_block_so_a_fresh_prefill_is_never_evicted():
+    """a prompt whose length is a multiple of the block size needs a new block per layer for its first
+    decoded token.  With only the prompt's blocks free, admitting it would make the very next step run out of
+    blocks and the eviction rule would drop the request that was just prefilled; it must wait in `pending`."""
+    B, L = 4, 2
+    kv = make(S=2, L=L, MB=6, B=B, num_blocks=2 * L + 2 * L + 1)          # 9 blocks
+    sch = BatchedScheduler(StubModel(), kv, max_length=10)
+    a = sch.add_sequence(list(range(1, 8)))       # 7 tokens: 2 blocks/layer = 4 blocks; 5 free
+    assert a in sch.row_of and len(kv.free_blocks) == 5
+    # 8 tokens = 2 full blocks/layer = 4 blocks, and its first decoded token opens a third (2 more): 6 > 5 free
+    b = sch.add_sequence(list(range(10, 18)))
+    assert b not in sch.row_of and len(sch.pending) == 1, "admitted without room for its first decode step"
+    sch.run()
+    assert sch.finished[a] == "max_length" and sch.finished[b] == "max_length"      # b ran once a's blocks came back
+    assert sch.sequences[b] == expected(list(range(10, 18)), 10)
+    assert "evicted" not in sch.finished.values()
+
+
+def test_max_length_is_clamped_to_the_models_position_table():
+    """positions index wpe, which has n_positions rows; the scheduler must never run past it."""
+    class Shaped(StubModel):
+        class shape:
+            n_positions = 9
+    kv = make(S=1, MB=6, B=4)                     # table capacity 24 tokens
+    sch = BatchedScheduler(Shaped(), kv, max_length=20)
+    assert sch.max_length == 9
+    s = sch.add_sequence([1, 2, 3])
+    sch.run()
+    assert len(sch.sequences[s]) == 9 and sch.finished[s] == "max_length"
+    too_long = sch.add_sequence(list(range(10)))  # longer than the position table: can never run
+    sch.run()
+    assert sch.finished[too_long] == "evicted"

@@ -50,7 +50,10 @@ def _worker(rank, world, port, out_dir):
         state = {"transformer.wte.weight": wte, "lm_head.weight": wte,               # tied
                  "h.0.ln.weight": torch.randn(16), "h.0.attn.w": torch.randn(16, 48).half(),
                  "h.0.attn.b": torch.randn(48).half(), "step": torch.tensor([rank], dtype=torch.int64)}
+        assert not sharding.replicas_agree(state)            # ... and the checksum all_reduce sees it
         sharding.broadcast_state_dict(state, src=0, bucket_bytes=1024)   # small buckets: exercise the splitting
+        assert sharding.replicas_agree(state)                # one all_reduce: every rank holds rank 0's weights now
+        assert sharding.reduce_sum([1.0 + rank, 2.0], torch.device("cpu")) == [3.0, 4.0]
         torch.manual_seed(100)
         wte0 = torch.randn(50, 16)
         assert torch.equal(state["transformer.wte.weight"], wte0)
@@ -65,7 +68,7 @@ def _worker(rank, world, port, out_dir):
         model.load_state_dict(synthetic_gpt2_state_dict(shape, seed=rank))
         model.broadcast_weights(src=0)
         wte_rank0 = synthetic_gpt2_state_dict(shape, seed=0)["transformer.wte.weight"]
-        assert torch.equal(model.w["transformer.wte.weight"], wte_rank0)
+        assert torch.equal(model.w["transformer.wte.weight"], wte_rank0) and sharding.replicas_agree(model.state_dict())
         assert model._lm_head_padded.shape == (64, 16) and torch.equal(model._lm_head_padded[:37], wte_rank0)
         assert not model._lm_head_padded[37:].any()
         # request sharding + host-side gather of results

@@ -19,10 +19,10 @@ echo "bench ref rc=$?"; cat gpurun_out/bench_ref.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-model --no-extras > gpurun_out/ncu_launch_bench.log 2>&1
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-model --no-extras --no-configs > gpurun_out/ncu_launch_bench.log 2>&1
 echo "ncu launches rc=$?"; tail -2 gpurun_out/ncu_launch_bench.log | cut -c1-300
 echo "== ncu full capture of the attention kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pa_v1_kernel -s 40 -c 3 -f -o gpurun_out/prof_pa_v1 \
-   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-model --no-extras > gpurun_out/ncu_full_bench.log 2>&1
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-model --no-extras --no-configs > gpurun_out/ncu_full_bench.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep
 fi

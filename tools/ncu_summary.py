@@ -93,9 +93,19 @@ def main():
         launches(a.launches, os.path.join(ROOT, "profiles", f"{a.tag}_launches.md"), a.cmd)
     if os.path.isfile(a.rep):
         rd, wr = full(a.rep, os.path.join(ROOT, "profiles", f"{a.tag}_pa_v1_metrics.csv"))
+        try:
+            commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True,
+                                    text=True).stdout.strip() or "unknown"
+        except Exception:
+            commit = "unknown"
+        import sys
+        sys.path.insert(0, ROOT)
+        from vllmini_b200 import _native
         with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
             json.dump({"pa_v1_dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
                        "source": f"profiles/{a.tag}_pa_v1_metrics.csv (ncu --set full, mean of captured launches)",
+                       "kernel": _native.plan(256, 12, 12, 64, 16, 1024).split(" grid")[0],
+                       "commit": f"{commit} (+ working tree at capture time)",
                        "workload": "bs=256 ctx=1024 12x64 block 16"}, f, indent=1)
         print("traffic per launch: read %.1f MB write %.1f MB" % (rd / 1e6, wr / 1e6))
 

@@ -49,21 +49,32 @@ def run(fn, T, H, D, B, contiguous_slots, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_cache.json"))
+    ap.add_argument("--modes", default="0", help="experiments build only: 0 shipped dispatch, 1 warp kernel, "
+                                                 "2 16-token tiles, 3 32-token tiles")
     a = ap.parse_args()
     from helpers import load_ref_extension
+    from vllmini_b200 import _native
     ref = load_ref_extension()
+    modes = [int(m) for m in a.modes.split(",")]
+    set_mode = None
+    if modes != [0]:
+        set_mode = _native.load().vb200_debug_set_cache_kernel       # AttributeError on the shipped library
+    cases = [(f"{'prefill' if c else 'decode'} T={T}", T, c) for T in (256, 512, 1024, 2048, 4096, 16384)
+             for c in (False, True)] + [("prefill T=131072", 131072, True)]
     res = []
-    for name, T, contiguous in (("decode bs=256", 256, False), ("decode bs=2048", 2048, False),
-                                ("prefill 1024 tok", 1024, True), ("prefill 16384 tok", 16384, True),
-                                ("prefill 131072 tok", 131072, True)):
-        for B in (16,):
-            us_new = run(ops.reshape_and_cache, T, 12, 64, B, contiguous)
-            us_ref = run(ref.cache_ops.reshape_and_cache, T, 12, 64, B, contiguous) if ref is not None else None
+    for name, T, contiguous in cases:
+        us_ref = run(ref.cache_ops.reshape_and_cache, T, 12, 64, 16, contiguous) if ref is not None else None
+        for mode in modes:
+            if set_mode:
+                set_mode(mode)
+            us_new = run(ops.reshape_and_cache, T, 12, 64, 16, contiguous)
             byts = 4 * T * 12 * 64 * 2
-            r = dict(case=name, T=T, block_size=B, us_new=us_new, us_ref=us_ref, gbps_new=byts / us_new / 1e3,
-                     gbps_ref=(byts / us_ref / 1e3) if us_ref else None)
+            r = dict(case=name, T=T, contiguous=contiguous, mode=mode, us_new=us_new, us_ref=us_ref,
+                     speedup=(us_ref / us_new) if us_ref else None, gbps_new=byts / us_new / 1e3)
             res.append(r)
             print(json.dumps(r), flush=True)
+    if set_mode:
+        set_mode(0)
     with open(a.out, "w") as f:
         json.dump(res, f, indent=1)
 

@@ -18,14 +18,16 @@
 namespace vb200 {
 
 // x == 8, head_size % 8 == 0, 16-byte aligned rows.
-// One CTA per (32-token tile, head).  Phase 1: the tile's K and V rows (32 x D halves each) are read with
-// coalesced 128-bit loads -- issued before the slots are known, so the slot load and the data loads overlap --
-// and parked in shared memory (row pitch D*2+16 bytes: conflict-free for both access patterns below).
-// Phase 2: lane <-> token.  K: lane stores the 16-byte group g of its token to key_cache[blk][h][g][off][0..7];
-// V: lane stores element d of its token to value_cache[blk][h][d][off].  When consecutive tokens occupy
-// consecutive slots of a block (prefill) the lanes of a store instruction hit consecutive addresses and the
-// LSU coalesces them into whole sectors; with scattered slots (decode) every store is its own sector, which is
-// what the layout dictates.  No run detection, no alignment requirement on the slots.
+// One CTA per (16/32-token tile, head).  The tile's slots are read first and classified (warp ballot):
+//  * consecutive slots (prefill).  Phase 1: the tile's K and V rows (D halves each) are read with coalesced
+//    128-bit loads and parked in shared memory (row pitch D*2+16 bytes: conflict-free for both access patterns).
+//    Phase 2: lane <-> token.  K: lane stores the 16-byte group g of its token to key_cache[blk][h][g][off][0..7];
+//    V: lane stores element d of its token to value_cache[blk][h][d][off]: the lanes of a store instruction hit
+//    consecutive addresses and the LSU coalesces them into whole sectors.
+//  * scattered slots (a large decode batch): every store is its own sector whatever the mapping -- that is what
+//    the layout dictates -- so the rows go straight from registers to the caches, warp <-> token, without the
+//    staging pass and its CTA barrier (the staged fallback of round 1 lost to the reference kernel here, 14.2 vs
+//    13.2 us at 2048 tokens).
 constexpr int kTileThreads = 128;
 
 template <int kTileTokens>   // 32, or 16 for small batches (more CTAs in flight)
@@ -52,8 +54,58 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
   const int my_tok = t0 + lane;
   const int64_t slot = (lane < kTileTokens && my_tok < num_tokens) ? slot_mapping[my_tok] : -1;
 
-  // ---- phase 1: coalesced 128-bit row loads -> smem.  All loads of a batch are issued before the first store
-  //      so a thread pays one memory round trip per batch (the slot load above overlaps too). ----
+  // Are the tile's tokens (mostly) in consecutive slots?  Every warp holds the same slots -> same answer.
+  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
+  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && slot >= 0 && slot == prev + 1);
+  const bool run_like = __popc(adj) >= kTileTokens / 2;
+
+  if (!run_like) {
+    // ---- decode-like (scattered slots): no staging, no CTA barrier.  warp <-> token, lanes <-> 32-bit words of the
+    //      row, so the stores of one instruction stay inside one (block, head) tile; the rows of all of this warp's
+    //      tokens are loaded before the first store (one memory round trip after the slots). ----
+    constexpr int kTok = kTileTokens / (kTileThreads / 32);   // tokens per warp
+    constexpr int kMaxWords = 4;                              // head_size <= 256
+    uint32_t kw[kTok][kMaxWords], vw[kTok][kMaxWords];
+#pragma unroll
+    for (int n = 0; n < kTok; ++n) {
+      const int tok = warp + n * (kTileThreads / 32);
+      const bool live = t0 + tok < num_tokens;
+      const uint32_t* krow = reinterpret_cast<const uint32_t*>(key + (int64_t)(t0 + tok) * key_stride + (int64_t)h * head_size);
+      const uint32_t* vrow = reinterpret_cast<const uint32_t*>(value + (int64_t)(t0 + tok) * value_stride + (int64_t)h * head_size);
+#pragma unroll
+      for (int u = 0; u < kMaxWords; ++u) {
+        const int i = lane + 32 * u;
+        if (live && i < head_size / 2) {
+          kw[n][u] = __ldg(krow + i);
+          vw[n][u] = __ldg(vrow + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kTok; ++n) {
+      const int tok = warp + n * (kTileThreads / 32);
+      const int64_t s_tok = __shfl_sync(0xffffffffu, slot, tok);
+      if (s_tok < 0) continue;   // padding token (cache_kernels.cu:166-169); also tokens past num_tokens
+      const int64_t blk = s_tok / block_size;
+      const int off = (int)(s_tok % block_size);
+      uint32_t* kdst32 = reinterpret_cast<uint32_t*>(key_cache + (blk * num_heads + h) * (int64_t)head_size * block_size);
+      uint16_t* vdst =
+          reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
+#pragma unroll
+      for (int u = 0; u < kMaxWords; ++u) {
+        const int i = lane + 32 * u;   // 32-bit word i of the row: dims 2i, 2i+1
+        if (i < head_size / 2) {
+          kdst32[((int64_t)(i >> 2) * block_size + off) * 4 + (i & 3)] = kw[n][u];
+          vdst[(int64_t)(2 * i) * block_size] = (uint16_t)(vw[n][u] & 0xffffu);
+          vdst[(int64_t)(2 * i + 1) * block_size] = (uint16_t)(vw[n][u] >> 16);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- prefill-like.  Phase 1: coalesced 128-bit row loads -> smem.  All loads of a batch are issued before the
+  //      first store so a thread pays one memory round trip per batch. ----
   const int nchunks = kTileTokens * groups;
   constexpr int kBatch = 4;
   for (int c0 = threadIdx.x; c0 < nchunks; c0 += kTileThreads * kBatch) {
@@ -83,49 +135,21 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
   }
   __syncthreads();
 
-  // Are the tile's tokens (mostly) in consecutive slots?  Every warp holds the same slots -> same answer.
-  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
-  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && slot >= 0 && slot == prev + 1);
-  const bool run_like = __popc(adj) >= kTileTokens / 2;
-
-  if (run_like) {
-    // ---- prefill-like: lane <-> token, so one store instruction covers consecutive slots ----
-    if (slot < 0) return;  // padding token (cache_kernels.cu:166-169); also lanes past num_tokens
-    const int64_t blk = slot / block_size;
-    const int off = (int)(slot % block_size);
-    __half* kdst = key_cache + ((blk * num_heads + h) * (int64_t)groups * block_size + off) * 8;
-    for (int g = warp; g < groups; g += kTileThreads / 32)
-      *reinterpret_cast<uint4*>(kdst + (int64_t)g * block_size * 8) =
-          *reinterpret_cast<const uint4*>(ks + lane * pitch + g * 16);
-    uint16_t* vdst =
-        reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
-    const uint32_t* vrow = vs + lane * vpitch;
-    for (int d2 = warp; d2 < head_size / 2; d2 += kTileThreads / 32) {
-      const uint32_t w = vrow[d2];
-      vdst[(int64_t)(2 * d2) * block_size] = (uint16_t)(w & 0xffffu);
-      vdst[(int64_t)(2 * d2 + 1) * block_size] = (uint16_t)(w >> 16);
-    }
-  } else {
-    // ---- decode-like (scattered slots): warp <-> token, lanes <-> head dims, so the stores of one
-    //      instruction stay inside one (block, head) tile instead of 32 different blocks ----
-    for (int tok = warp; tok < kTileTokens; tok += kTileThreads / 32) {
-      const int64_t s_tok = __shfl_sync(0xffffffffu, slot, tok);
-      if (s_tok < 0) continue;
-      const int64_t blk = s_tok / block_size;
-      const int off = (int)(s_tok % block_size);
-      uint32_t* kdst32 = reinterpret_cast<uint32_t*>(key_cache + (blk * num_heads + h) * (int64_t)head_size * block_size);
-      uint16_t* vdst =
-          reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
-      const uint32_t* krow = reinterpret_cast<const uint32_t*>(ks + tok * pitch);
-      const uint32_t* vrow = vs + tok * vpitch;
-      for (int i = lane; i < head_size / 2; i += 32) {   // 32-bit word i of the row: dims 2i, 2i+1
-        const int g = i >> 2, part = i & 3;
-        kdst32[((int64_t)g * block_size + off) * 4 + part] = krow[i];
-        const uint32_t w = vrow[i];
-        vdst[(int64_t)(2 * i) * block_size] = (uint16_t)(w & 0xffffu);
-        vdst[(int64_t)(2 * i + 1) * block_size] = (uint16_t)(w >> 16);
-      }
-    }
+  // ---- phase 2: lane <-> token, so one store instruction covers consecutive slots ----
+  if (slot < 0) return;  // padding token (cache_kernels.cu:166-169); also lanes past num_tokens
+  const int64_t blk = slot / block_size;
+  const int off = (int)(slot % block_size);
+  __half* kdst = key_cache + ((blk * num_heads + h) * (int64_t)groups * block_size + off) * 8;
+  for (int g = warp; g < groups; g += kTileThreads / 32)
+    *reinterpret_cast<uint4*>(kdst + (int64_t)g * block_size * 8) =
+        *reinterpret_cast<const uint4*>(ks + lane * pitch + g * 16);
+  uint16_t* vdst =
+      reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
+  const uint32_t* vrow = vs + lane * vpitch;
+  for (int d2 = warp; d2 < head_size / 2; d2 += kTileThreads / 32) {
+    const uint32_t w = vrow[d2];
+    vdst[(int64_t)(2 * d2) * block_size] = (uint16_t)(w & 0xffffu);
+    vdst[(int64_t)(2 * d2 + 1) * block_size] = (uint16_t)(w >> 16);
   }
 }
 
@@ -197,6 +221,20 @@ __global__ void __launch_bounds__(256) reshape_and_cache_generic_kernel(
 
 using namespace vb200;
 
+#ifdef VB200_EXPERIMENTS
+// sweep knob of the experiments build (tools/sweep_cache.py): 0 = shipped dispatch, 1 = warp kernel for any size,
+// 2 = 16-token tiles, 3 = 32-token tiles
+static int g_cache_mode = 0;
+extern "C" int32_t vb200_debug_set_cache_kernel(int32_t mode) {
+  const int prev = g_cache_mode;
+  g_cache_mode = mode;
+  return prev;
+}
+static int cache_mode() { return g_cache_mode; }
+#else
+static constexpr int cache_mode() { return 0; }
+#endif
+
 extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, void* key_cache, void* value_cache,
                                            const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
                                            int32_t head_size, int32_t block_size, int32_t x, int64_t key_stride,
@@ -216,7 +254,8 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
   const bool vec_ok = x == 8 && head_size % 8 == 0 && key_stride % 8 == 0 && value_stride % 8 == 0 &&
                       ((((uintptr_t)key | (uintptr_t)value | (uintptr_t)key_cache) & 15) == 0);
   if (vec_ok && head_size <= 256 && (num_tokens + 15) / 16 <= 65535) {
-    if (num_tokens <= 512) {  // decode-sized: latency-bound, skip the shared-memory transpose
+    const int mode = cache_mode();
+    if (mode == 1 || (mode == 0 && num_tokens <= 512)) {  // decode-sized: latency-bound, one warp per (token, head)
       const int64_t warps = (int64_t)num_tokens * num_heads;
       VB200_CUDA_CHECK(launch_kernel(reshape_and_cache_warp_kernel, dim3((unsigned)((warps + 3) / 4)), dim3(128), 0, s,
                                      static_cast<const __half*>(key), static_cast<const __half*>(value),
@@ -225,7 +264,7 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
       count_launch();
       return VB200_OK;
     }
-    const int tt = num_tokens <= 2048 ? 16 : 32;   // small batches: smaller tiles, more CTAs in flight
+    const int tt = mode == 2 ? 16 : mode == 3 ? 32 : (num_tokens <= 2048 ? 16 : 32);   // small batches: smaller tiles
     const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
     dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
     auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16> : reshape_and_cache_tile_kernel<32>;
