@@ -22,7 +22,7 @@ from vllmini_b200 import ops  # noqa: E402
 def run(fn, T, H, D, B, contiguous_slots, iters=20):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
-    NB = max((T + B - 1) // B * 4, 4096)
+    NB = max((T + B - 1) // B * 4, 4096) if contiguous_slots else max(2 * T, 4096)   # scattered: one block per token
     qkv = torch.randn(T, 3 * H * D, generator=g, device=dev, dtype=torch.float16)
     k, v = qkv[:, H * D:2 * H * D].view(T, H, D), qkv[:, 2 * H * D:].view(T, H, D)
     kc = torch.zeros(NB, H, D // 8, B, 8, dtype=torch.float16, device=dev)
