@@ -48,7 +48,7 @@ def test_plan_names_the_launched_instantiation():
     assert _native.plan(256, 12, 12, 64, 16, 1024) == \
         "vb200::pa_v1_kernel<64,16,4,2,0> grid=(12,256,1) block=128 smem=67040"
     assert "pa_v1_kernel<64,16,4,2,1>" in _native.plan(256, 12, 12, 64, 16, 1024, fused_append=True)
-    assert "grid=(12,1,22)" in _native.plan(1, 12, 12, 64, 16, 8192)                  # small batch: split-KV
+    assert "grid=(12,1,16)" in _native.plan(1, 12, 12, 64, 16, 8192)                  # small batch: split-KV cluster
     assert "pa_v1_gqa_kernel<128,16,4,1,0,4> grid=(8,256,1)" in _native.plan(256, 32, 8, 128, 16, 1024)
     assert "pa_v1_kernel<128,16,3,2,0>" in _native.plan(8, 32, 8, 128, 16, 1024)      # small batch: per-head grid
     with pytest.raises(RuntimeError, match="Unsupported head size"):
@@ -110,7 +110,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.vb200_reshape_and_cache_f16(one, one, one, one, one, 1, 12, 64, 16, 7, 768, 768, 0, None) == -4
     assert lib.vb200_reshape_and_cache_f16(None, one, one, one, one, 1, 12, 64, 16, 8, 768, 768, 0, None) == -4
     assert lib.vb200_paged_attention_v1_workspace_bytes(256, 12, 64, 16, 1024) == 0      # big batch: never splits
-    assert lib.vb200_paged_attention_v1_workspace_bytes(1, 12, 64, 16, 8192) > 16384 * 4  # tiny batch: split-KV partials
+    assert lib.vb200_paged_attention_v1_workspace_bytes(1, 12, 64, 16, 8192) == 0        # splits merge in a cluster
     two = ctypes.cast(ctypes.c_void_p(16), ctypes.c_void_p)
     def v2(**kw):
         a = dict(block_size=16, head_size=64, msl=1024)

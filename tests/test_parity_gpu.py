@@ -201,7 +201,6 @@ def test_two_streams_splitting_concurrently_do_not_share_a_workspace():
                 ops.paged_attention_v1(o[i], t[0], t[1], t[2], 12, 0.125, t[3], t[4], 16, msl, None, "auto", 1.0,
                                        0, 0, 1, 1, 0)
     torch.cuda.synchronize()
-    assert len({k[:2] for k in ops._workspaces if k[0] == 0} | set()) >= 2 or ops.BINDING == "torch_shim"
     for (t, truth, _msl), o in zip(cases, outs):
         for i in range(40):
             assert_close_to_truth(o[i].cpu().numpy(), truth, what=f"stream-concurrent split-KV, call {i}")
@@ -215,8 +214,8 @@ def test_small_batch_long_context_uses_split_kv():
     q, kc, vc, bt, sl = po.make_case(2, 12, 64, 16, lens, seed=21)
     c = dict(S=2, H=12, D=64, B=16, q=q, kc=kc, vc=vc, bt=bt, sl=sl, scale=0.125)
     from vllmini_b200 import _native
-    assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) > 16384 * 4
-    assert _native.load().vb200_paged_attention_v1_workspace_bytes(256, 12, 64, 16, 1024) == 0    # never splits
+    assert "grid=(12,2,13)" in _native.plan(2, 12, 12, 64, 16, int(bt.shape[1]) * 16)             # 13 splits, one cluster each
+    assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) == 0
     got = run_cuda_attention(c)
     truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, mode="exact").astype(np.float64)
     assert_close_to_truth(got, truth, what="split-KV")

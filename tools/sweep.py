@@ -85,7 +85,7 @@ def make(S, H, D, B, ctx, seed, dev, mixed=False, QH=None):
     return q, kc, vc, bt, lens
 
 
-def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
+def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False, merge=0, max_cluster=16):
     S, H, D, B, ctx = CONFIGS[name][:5]
     QH = CONFIGS[name][5] if len(CONFIGS[name]) > 5 else None
     mixed = ctx < 0
@@ -97,6 +97,8 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
     outs = [torch.empty_like(p[0]) for p in pools]
     if splits or variant:          # sweep knobs: needs the experiments build (VLLMINI_B200_LIB=.../lib/experiments/...)
         _native.set_tuning(splits, variant)
+    if merge or max_cluster != 16:
+        _native.set_merge(merge, max_cluster)
     def call(i):
         q, kc, vc, bt, sl = pools[i % npools]
         if ref is None:
@@ -136,9 +138,12 @@ def time_config(name, variant, splits, iters=20, warm=5, ref=None, graph=False):
     ab = sum(algorithmic_bytes(S, H, D, B, p[4].tolist()) for p in pools) / npools
     if splits or variant:
         _native.set_tuning(0, 0)
+    if merge or max_cluster != 16:
+        _native.set_merge(0, 16)
     del pools, outs
     torch.cuda.empty_cache()
-    return dict(config=name, variant=variant, splits=splits, us_median=med, us_min=ts[0], gbps=ab / med / 1e3,
+    return dict(config=name, variant=variant, splits=splits, merge="workspace" if merge else "cluster",
+                max_cluster=max_cluster, us_median=med, us_min=ts[0], gbps=ab / med / 1e3,
                 bytes=ab, impl="ref" if ref is not None else "new", timing="graph" if graph else "events")
 
 
@@ -150,6 +155,8 @@ def main():
     ap.add_argument("--ref", action="store_true", help="also time the reference's own kernel (oracle/_ref)")
     ap.add_argument("--pool-mult", type=int, default=1)
     ap.add_argument("--graph", action="store_true", help="time launches replayed from a CUDA graph (no host overhead)")
+    ap.add_argument("--merge", default="0", help="experiments build: 0 cluster merge, 1 workspace merge (comma list)")
+    ap.add_argument("--max-cluster", default="16", help="experiments build: cap on the cluster size (comma list)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     a = ap.parse_args()
     global POOL_MULT
@@ -163,9 +170,13 @@ def main():
     for name in a.configs.split(","):
         for v in [int(x) for x in a.variants.split(",")]:
             for sp in [int(x) for x in a.splits.split(",")]:
-                r = time_config(name, v, sp, graph=a.graph)
-                res.append(r)
-                print(json.dumps(r), flush=True)
+                for mg in [int(x) for x in a.merge.split(",")]:
+                    for mc in [int(x) for x in a.max_cluster.split(",")]:
+                        if mg == 0 and sp > mc:
+                            continue          # a cluster cannot be larger than its cap
+                        r = time_config(name, v, sp, graph=a.graph, merge=mg, max_cluster=mc)
+                        res.append(r)
+                        print(json.dumps(r), flush=True)
         if ref is not None:
             r = time_config(name, 0, 0, ref=ref, graph=a.graph)
             res.append(r)

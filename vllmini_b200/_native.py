@@ -112,3 +112,14 @@ def set_tuning(force_num_splits: int = 0, variant: int = 0) -> int:
     fn = lib.vb200_debug_set_tuning
     fn.restype, fn.argtypes = _i32, [_i32, _i32]
     return int(fn(int(force_num_splits), int(variant)))
+
+
+def set_merge(merge_mode: int = 0, max_cluster: int = 16) -> None:
+    """Experiments build only: split-KV merge through the thread-block cluster (0, shipped) or through round 1's
+    workspace + last-arriver path (1); cap on the cluster size."""
+    lib = load()
+    if not has_experiments():
+        raise RuntimeError("vllmini_b200: this build has no sweep knobs (see set_tuning)")
+    fn = lib.vb200_debug_set_merge
+    fn.restype, fn.argtypes = None, [_i32, _i32]
+    fn(int(merge_mode), int(max_cluster))

@@ -57,27 +57,46 @@ struct DeviceGuard {
 bool pdl_enabled();                // abi.cu (vb200_set_pdl)
 void disable_pdl();
 
+// cluster_z > 1 launches thread-block clusters of (1, 1, cluster_z) CTAs (grid.z must be a multiple of it).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 Args... args) {
+inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t stream, unsigned cluster_z, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 1;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = cluster_z;
+    ++n;
+  }
+  const int n_fixed = n;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-  if (e == cudaErrorNotSupported && cfg.numAttrs) {  // driver / capture mode without programmatic launches
+  if (e == cudaErrorNotSupported && n > n_fixed) {  // driver / capture mode without programmatic launches
     cudaGetLastError();
     disable_pdl();
-    cfg.numAttrs = 0;
+    cfg.numAttrs = n_fixed;
     e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   }
   return e;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  return launch_kernel_cluster(kern, grid, block, smem, stream, 1u, args...);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -92,6 +111,24 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- thread-block cluster: barrier over all CTAs of the cluster, distributed shared memory ----
+// (release/acquire: shared-memory writes before the arrive are visible to every CTA of the cluster after the wait)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // ---- mbarrier (shared::cta) ----

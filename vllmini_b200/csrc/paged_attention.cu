@@ -50,6 +50,8 @@ struct PaParams {
   float scale_log2e;
   int num_splits;
   int split_tokens;  // multiple of 32; ignored when num_splits == 1
+  int cluster_merge; // != 0: the num_splits CTAs of a (seq, head) form one thread-block cluster (1, 1, num_splits) and
+                     // merge their partials through distributed shared memory -- no workspace, no counters
   int32_t* ws_cnt;   // [num_seqs * num_heads] zero between launches
   float* ws_ml;      // [num_seqs * num_heads * num_splits * 2]
   float* ws_o;       // [num_seqs * num_heads * num_splits * D]
@@ -272,7 +274,7 @@ __device__ __forceinline__ void warp_publish(float* red, int warp, int lane, flo
 // `tid` in [0, W*32); BAR = named barrier id used by the W*32 compute threads.
 template <class C, int W, int BAR>
 __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const float* red, int tid, int seq, int head,
-                                                    int split, int nsplit_seq, int* s_last) {
+                                                    int split, int nsplit_seq, int* s_last, float* part) {
   constexpr int D = C::kD;
   float M = -INFINITY;
 #pragma unroll
@@ -303,6 +305,46 @@ __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const flo
       p.v2_max_logits[part_idx] = M * 0.69314718055994530942f;  // log2 domain -> natural log
       p.v2_exp_sums[part_idx] = L;
     }
+    return;
+  }
+
+  if (p.cluster_merge) {
+    // ---- split-KV inside a thread-block cluster: every CTA of the cluster (also one whose split holds no token)
+    //      parks its partial {o[D], M, L} in its own shared memory (`part`: the start of the ring, idle by now),
+    //      a cluster barrier publishes them, the CTA of split 0 merges the live splits through distributed shared
+    //      memory and writes the row, and a second barrier keeps every CTA's shared memory alive until then. ----
+    for (int d = tid; d < D; d += W * 32) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
+      part[d] = o;
+    }
+    if (tid == 0) {
+      part[D] = M;
+      part[D + 1] = L;
+    }
+    cluster_sync_all();
+    if (split == 0) {
+      const uint32_t base = smem_u32(part);
+      float Mg = -INFINITY;
+      for (int i = 0; i < nsplit_seq; ++i) Mg = fmaxf(Mg, ld_dsmem_f32(dsmem_addr(base + D * 4, i)));
+      float Lg = 0.f;
+      for (int i = 0; i < nsplit_seq; ++i) {
+        const float mi = ld_dsmem_f32(dsmem_addr(base + D * 4, i));
+        Lg += ld_dsmem_f32(dsmem_addr(base + (D + 1) * 4, i)) * ((mi == -INFINITY) ? 0.f : ex2(mi - Mg));
+      }
+      const float inv = __fdividef(1.f, Lg + 1e-6f);   // reference normaliser (attention_kernels.cu:342)
+      for (int d = tid; d < D; d += W * 32) {
+        float o = 0.f;
+        for (int i = 0; i < nsplit_seq; ++i) {
+          const float mi = ld_dsmem_f32(dsmem_addr(base + D * 4, i));
+          const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
+          o += ld_dsmem_f32(dsmem_addr(base + d * 4, i)) * wi;
+        }
+        p.out[row * D + d] = __float2half_rn(o * inv);
+      }
+    }
+    cluster_sync_all();
     return;
   }
 
@@ -425,12 +467,23 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   }
   griddep_wait();
 
+  // The table entries of this warp's first ring do not depend on seq_len: fetch them together with it (one
+  // dependent memory round trip less in front of the first bulk copy).  Reading inside the table row is always
+  // safe; entries beyond the sequence's blocks are fetched but never used.
+  const int blk_begin = (p.num_splits > 1 || p.v2_exp_sums != nullptr) ? split * (p.split_tokens / B) : 0;
+  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + blk_begin;
+  int ph[NST];
+#pragma unroll
+  for (int k = 0; k < NST; ++k) {
+    const int blk = (warp + k * W) * C::BPS + lane;
+    ph[k] = (lane < C::BPS && blk_begin + blk < p.max_blocks_per_seq) ? __ldg(table + blk) : 0;
+  }
   const UnitRange r = unit_range<B>(p, seq, split);
-  if (r.empty_split) return;
+  // a split without tokens has nothing to do -- unless its cluster waits for it at the merge barriers
+  if (r.empty_split && !p.cluster_merge) return;
   const int nstages = r.nstages, nblk = r.nblk;
 
   const int kv_head = head / (p.num_heads / p.num_kv_heads);
-  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + r.tok_begin / B;
   const __half* kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
   const __half* vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
 
@@ -476,15 +529,10 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
     return (lane < C::BPS && blk < nblk) ? __ldg(table + blk) : 0;
   };
 
-  // prologue: fill the ring
-  {
-    int ph[NST];
+  // prologue: fill the ring (table entries prefetched above)
 #pragma unroll
-    for (int k = 0; k < NST; ++k) ph[k] = (warp + k * W < nstages) ? load_phys(warp + k * W) : 0;
-#pragma unroll
-    for (int k = 0; k < NST; ++k)
-      if (warp + k * W < nstages) issue_stage(warp + k * W, k, ph[k]);
-  }
+  for (int k = 0; k < NST; ++k)
+    if (warp + k * W < nstages) issue_stage(warp + k * W, k, ph[k]);
   int next_phys = (warp + NST * W < nstages) ? load_phys(warp + NST * W) : 0;
 
   // ---- q: dims 8*(lane/B + j*BPS) .. +7 of this head's row, packed fp16 ----
@@ -565,7 +613,8 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   float* red = reinterpret_cast<float*>(smem + C::RED_OFF);  // [W][D + 2]
   warp_publish<C>(red, warp, lane, m, lsum, acc);
   __syncthreads();
-  cta_merge_and_store<C, W, 1>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, &s_last);
+  cta_merge_and_store<C, W, 1>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, &s_last,
+                               reinterpret_cast<float*>(smem));
 #ifdef VB200_TRACE
   if (threadIdx.x == 0 && p.trace != nullptr) {
     unsigned long long t_end;
@@ -844,7 +893,8 @@ __global__ void __launch_bounds__(W * 32, PaCfgG<D, B, W, NST, G>::CTAS_PER_SM) 
   for (int g = 0; g < G; ++g) warp_publish<C>(red + g * (W * (D + 2)), warp, lane, m[g], lsum[g], acc[g]);
   __syncthreads();
   for (int g = 0; g < G; ++g)
-    cta_merge_and_store<C, W, 1>(p, red + g * (W * (D + 2)), threadIdx.x, seq, head0 + g, split, r.nsplit_seq, &s_last);
+    cta_merge_and_store<C, W, 1>(p, red + g * (W * (D + 2)), threadIdx.x, seq, head0 + g, split, r.nsplit_seq, &s_last,
+                                 reinterpret_cast<float*>(smem));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -910,6 +960,8 @@ struct Shape {
 struct Tuning {
   int force_splits = 0;
   int variant = 0;
+  int merge_mode = 0;    // 0: cluster merge (shipped behaviour), 1: workspace + last-arriver merge (round-1 path)
+  int max_cluster = 16;  // cap on the cluster size / split factor of the cluster merge
 };
 static Tuning g_tuning;
 // 0: default; 1: 4x3; 2: 8x1; 3: 2x2; 4: default kernel with the grouped-query path off
@@ -917,9 +969,13 @@ static constexpr Shape kVariants[] = {{0, 2}, {4, 3}, {8, 1}, {2, 2}, {0, 2}};
 constexpr int kNumVariants = 5;
 static int tuning_variant() { return g_tuning.variant; }
 static int tuning_force_splits() { return g_tuning.force_splits; }
+static int tuning_merge_mode() { return g_tuning.merge_mode; }
+static int tuning_max_cluster() { return g_tuning.max_cluster; }
 #else
 static constexpr int tuning_variant() { return 0; }
 static constexpr int tuning_force_splits() { return 0; }
+static constexpr int tuning_merge_mode() { return 0; }
+static constexpr int tuning_max_cluster() { return 16; }
 #endif
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): a lock-free
@@ -959,11 +1015,65 @@ static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t str
   int dev = 0;
   VB200_CUDA_CHECK(cudaGetDevice(&dev));
   VB200_CUDA_CHECK(once.run(dev, [&] {
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // clusters of up to 16
   }));
-  VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream, p));
+  VB200_CUDA_CHECK(launch_kernel_cluster(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream,
+                                         p.cluster_merge ? (unsigned)p.num_splits : 1u, p));
   count_launch();
   return VB200_OK;
+}
+
+// Largest thread-block cluster (1, 1, z) the device can co-schedule for the default kernel of head size D (its
+// shared-memory footprint does not depend on the block size): 16 (non-portable, opt-in), else 8, 4, 2; 1 = none.
+// Queried once per device.
+template <int D>
+static int cluster_cap() {
+  constexpr int W = (D == 64 || D == 96 || D == 192) ? 4 : 3;
+  using C = PaCfg<D, 16, W, 2>;
+  auto kern = pa_v1_kernel<D, 16, W, 2, false>;
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return 1;
+  }
+  int cap = cached[dev].load(std::memory_order_acquire);
+  if (cap) return cap;
+  cap = 1;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) == cudaSuccess &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    for (unsigned z = 16; z >= 2 && cap == 1; z >>= 1) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(1, 1, z);
+      cfg.blockDim = dim3(W * 32);
+      cfg.dynamicSmemBytes = C::SMEM;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = z;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) cap = (int)z;
+    }
+  }
+  cudaGetLastError();
+  cached[dev].store(cap, std::memory_order_release);
+  return cap;
+}
+static int cluster_cap_for(int head_size) {
+  switch (head_size) {
+    case 64: return cluster_cap<64>();
+    case 80: return cluster_cap<80>();
+    case 96: return cluster_cap<96>();
+    case 112: return cluster_cap<112>();
+    case 128: return cluster_cap<128>();
+    case 192: return cluster_cap<192>();
+    default: return cluster_cap<256>();
+  }
 }
 
 // Default CTA shape per head size: W warps x 2 stages of 128*D bytes, W chosen so that the resident CTAs of an SM
@@ -1082,7 +1192,7 @@ static int heads_per_cta(int num_seqs, int num_heads, int num_kv_heads, int head
 // is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
 // `group` = query heads per CTA (heads_per_cta): the launch has num_seqs * num_heads / group units.
 static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq_len, int variant, int num_sms,
-                         int group, int* num_splits, int* split_tokens) {
+                         int group, int max_splits, int* num_splits, int* split_tokens) {
   const int64_t base = (int64_t)num_seqs * num_heads / group;
   int warps = default_warps(head_size);
 #ifdef VB200_EXPERIMENTS
@@ -1100,11 +1210,11 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
     if (ns > max_by_len) ns = max_by_len;
     if (ns > 64) ns = 64;
   }
+  if (ns > max_splits) ns = max_splits;
   if (ns < 1) ns = 1;
   int st = max_seq_len > 0 ? (max_seq_len + ns - 1) / ns : quantum;
   st = (st + quantum - 1) / quantum * quantum;
   ns = max_seq_len > 0 ? (max_seq_len + st - 1) / st : 1;
-  if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;   // one counter per (sequence, query head) row
   *num_splits = ns < 1 ? 1 : ns;
   *split_tokens = st;
 }
@@ -1124,17 +1234,11 @@ extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int
                                                            int32_t block_size, int32_t max_seq_len) {
   (void)block_size;
   if (num_seqs <= 0 || num_heads <= 0 || !head_size_supported(head_size)) return 0;
-  int variant = tuning_variant();
-  // num_kv_heads is not part of this query: size for whichever grouping the launch may pick
-  size_t bytes = 0;
-  for (int group = 1; group <= 4; group *= 2) {
-    if (num_heads % group != 0) continue;
-    int ns = 1, st = 0;
-    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, device_sm_count(), group, &ns, &st);
-    const size_t b = workspace_bytes_for(num_seqs, num_heads, head_size, ns);
-    bytes = b > bytes ? b : bytes;
-  }
-  return bytes;
+  if (tuning_merge_mode() == 0) return 0;   // split-KV merges inside a thread-block cluster: no scratch at all
+  int ns = 1, st = 0;
+  choose_split(num_seqs, num_heads, head_size, max_seq_len, tuning_variant(), device_sm_count(), 1, 64, &ns, &st);
+  if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;   // one counter per (sequence, query head) row
+  return workspace_bytes_for(num_seqs, num_heads, head_size, ns);
 }
 
 namespace {
@@ -1206,6 +1310,7 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.kv_block_stride = kv_block_stride;
   p.kv_head_stride = kv_head_stride;
   p.scale_log2e = (float)((double)scale * 1.4426950408889634074);
+  p.cluster_merge = 0;
   int ns = 1, st = 0;
   if (v2) {
     // the reference's fixed 512-token partitions; the partition count is the scratch tensors' stride
@@ -1214,11 +1319,19 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     ns = (max_seq_len + st - 1) / st;
     if (ns < 1) ns = 1;
     if (ns > 65535) return set_error(VB200_ERR_INVALID_ARGUMENT, "max_seq_len %d exceeds grid.z limit", max_seq_len);
-  } else {
+  } else if (group == 1 && max_seq_len > 0 && tuning_merge_mode() == 0) {
+    // split-KV, merged inside a thread-block cluster of the splits of a (sequence, head): no scratch, no state
+    int cap = planning ? 16 : cluster_cap_for(head_size);
+    if (cap > tuning_max_cluster()) cap = tuning_max_cluster();
+    choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, 1, cap, &ns, &st);
+    p.cluster_merge = ns > 1;
+  } else if (group == 1 && max_seq_len > 0) {
+    // experiments build only: round 1's workspace + last-arriver merge, kept for A/B measurements
     if (!planning && workspace != nullptr && (((uintptr_t)workspace & 15) || workspace_bytes < (size_t)kCounterCap * 4))
       workspace = nullptr;  // unusable scratch: run without split
-    if ((planning || workspace != nullptr) && max_seq_len > 0)
-      choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, group, &ns, &st);
+    if (planning || workspace != nullptr)
+      choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, 1, 64, &ns, &st);
+    if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;
     if (!planning && ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
   }
   p.num_splits = ns;
@@ -1374,5 +1487,10 @@ extern "C" int32_t vb200_debug_set_tuning(int32_t force_num_splits, int32_t vari
   g_tuning.force_splits = force_num_splits < 0 ? 0 : force_num_splits;
   g_tuning.variant = (variant < 0 || variant >= kNumVariants) ? 0 : variant;
   return prev;
+}
+// merge_mode 0: cluster merge, 1: round 1's workspace merge; max_cluster: cap on the cluster size (2..16)
+extern "C" void vb200_debug_set_merge(int32_t merge_mode, int32_t max_cluster) {
+  g_tuning.merge_mode = merge_mode ? 1 : 0;
+  g_tuning.max_cluster = max_cluster < 1 ? 16 : max_cluster;
 }
 #endif
