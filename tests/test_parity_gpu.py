@@ -207,14 +207,15 @@ def test_two_streams_splitting_concurrently_do_not_share_a_workspace():
 
 
 def test_small_batch_long_context_uses_split_kv():
-    """S*H far below the SM count: the launcher splits the context (flash-decoding style) and the
-    in-kernel last-arriver merge must reproduce the unsplit result."""
+    """S*H far below the SM count: the launcher splits the context (flash-decoding style) -- the splits of a
+    (sequence, head) form a thread-block cluster and merge through distributed shared memory -- and must reproduce
+    the unsplit result."""
     rng = np.random.default_rng(3)
     lens = np.array([4096, 3000], dtype=np.int32)
     q, kc, vc, bt, sl = po.make_case(2, 12, 64, 16, lens, seed=21)
     c = dict(S=2, H=12, D=64, B=16, q=q, kc=kc, vc=vc, bt=bt, sl=sl, scale=0.125)
     from vllmini_b200 import _native
-    assert "grid=(12,2,13)" in _native.plan(2, 12, 12, 64, 16, int(bt.shape[1]) * 16)             # 13 splits, one cluster each
+    assert "grid=(12,2,11)" in _native.plan(2, 12, 12, 64, 16, int(bt.shape[1]) * 16)             # 11 splits, one cluster each
     assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) == 0
     got = run_cuda_attention(c)
     truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, mode="exact").astype(np.float64)

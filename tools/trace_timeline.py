@@ -1,9 +1,8 @@
 #!/usr/bin/env python
 """CTA timeline of one paged_attention_v1 launch.  Needs a -DVB200_TRACE build of the library:
 
-    nvcc -shared -o vllmini_b200/lib/libvllmini_b200_trace.so -gencode arch=compute_100a,code=sm_100a -O3 \
-         -lineinfo -std=c++17 -Xcompiler -fPIC -DVB200_TRACE -Iinclude -Ivllmini_b200/csrc \
-         vllmini_b200/csrc/{abi,cache_kernels,cache_aux,paged_attention}.cu
+    python -m vllmini_b200.build --variant trace --define=-DVB200_TRACE
+    python tools/trace_timeline.py M C1            # or VB200_TRACE_LIB=<path to another trace build>
 
 Prints where the launch's wall time goes: ramp-up, steady state, tail; per-CTA prologue and lifetime."""
 import ctypes
@@ -19,7 +18,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 from sweep import CONFIGS, make  # noqa: E402
 
-lib = ctypes.CDLL(os.path.join(ROOT, "vllmini_b200", "lib", "libvllmini_b200_trace.so"))
+lib = ctypes.CDLL(os.environ.get("VB200_TRACE_LIB") or
+                  os.path.join(ROOT, "vllmini_b200", "lib", "trace", "libvllmini_b200.so"))
 vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 lib.vb200_paged_attention_v1_f16.argtypes = [vp] * 6 + [i32] * 7 + [i64] * 3 + [f32, vp, sz, i32, vp]
 lib.vb200_debug_set_trace.argtypes = [vp]
@@ -32,7 +32,7 @@ def run(name):
     ctx = abs(ctx)
     dev = torch.device("cuda:0")
     pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(2)]
-    nctas = S * H
+    nctas = S * H * 16          # room for a split launch (grid.z <= 16)
     trace = torch.zeros(nctas * 4, dtype=torch.int64, device=dev)
     ws = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -51,6 +51,9 @@ def run(name):
     call(0, trace.data_ptr())
     torch.cuda.synchronize()
     t = trace.cpu().numpy().reshape(nctas, 4).astype(np.int64)
+    t = t[t[:, 3] > 0]          # CTAs that ran (and recorded an end time)
+    nctas = len(t)
+    t[:, 2] = np.where(t[:, 2] > 0, t[:, 2], t[:, 1])    # a CTA without stages has no first-data time
     smid, t0, t1, t2 = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
     base = t0.min()
     t0, t1, t2 = (t0 - base) / 1e3, (t1 - base) / 1e3, (t2 - base) / 1e3     # us

@@ -39,12 +39,22 @@ def needs_build() -> bool:
 EXP_LIB_PATH = os.path.join(LIB_DIR, "experiments", "libvllmini_b200.so")
 
 
-def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
-    """experiments=True builds the sweep variant of the library (-DVB200_EXPERIMENTS: extra CTA shapes and a forced
-    split factor behind vb200_debug_set_tuning) to lib/experiments/; tools load it through VLLMINI_B200_LIB.  The
-    shipped library is always the default build."""
-    out_path = EXP_LIB_PATH if experiments else LIB_PATH
+def variant_path(name: str) -> str:
+    return os.path.join(LIB_DIR, name, "libvllmini_b200.so")
+
+
+def build(force: bool = False, verbose: bool = False, experiments: bool = False, variant: str = "",
+          defines=()) -> str:
+    """Default: the shipped library (vllmini_b200/lib/libvllmini_b200.so).
+
+    experiments=True builds the sweep variant (-DVB200_EXPERIMENTS: extra CTA shapes, forced split factor, merge
+    mode and cache-kernel knobs behind vb200_debug_* entries) to lib/experiments/; `variant` + `defines` build any
+    other development variant to lib/<variant>/ (e.g. "trace" with -DVB200_TRACE for tools/trace_timeline.py).
+    Tools load a variant through VLLMINI_B200_LIB; the product always loads the default build."""
     if experiments:
+        variant, defines = "experiments", ("-DVB200_EXPERIMENTS",) + tuple(defines)
+    out_path = variant_path(variant) if variant else LIB_PATH
+    if variant:
         deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
         if not force and os.path.isfile(out_path) and all(os.path.getmtime(d) <= os.path.getmtime(out_path) for d in deps):
             return out_path
@@ -63,8 +73,7 @@ def build(force: bool = False, verbose: bool = False, experiments: bool = False)
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    if experiments:
-        cmd += ["-DVB200_EXPERIMENTS"]
+    cmd += list(defines)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     print("+", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
@@ -112,9 +121,13 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--experiments", action="store_true", help="also build lib/experiments/ (sweep knobs)")
+    ap.add_argument("--variant", default="", help="also build lib/<variant>/ with the given --define flags")
+    ap.add_argument("--define", action="append", default=[], help="e.g. --define=-DVB200_TRACE")
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose))
     if a.experiments:
         print(build(force=a.force, verbose=a.verbose, experiments=True))
+    if a.variant:
+        print(build(force=a.force, verbose=a.verbose, variant=a.variant, defines=a.define))
     print(build_shim(force=a.force))
     sys.exit(0)

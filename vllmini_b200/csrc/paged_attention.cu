@@ -473,12 +473,21 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const int blk_begin = (p.num_splits > 1 || p.v2_exp_sums != nullptr) ? split * (p.split_tokens / B) : 0;
   const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + blk_begin;
   int ph[NST];
+#ifndef VB200_NO_SPEC_TABLE
 #pragma unroll
   for (int k = 0; k < NST; ++k) {
     const int blk = (warp + k * W) * C::BPS + lane;
     ph[k] = (lane < C::BPS && blk_begin + blk < p.max_blocks_per_seq) ? __ldg(table + blk) : 0;
   }
   const UnitRange r = unit_range<B>(p, seq, split);
+#else   // A/B builds only: the dependent order of round 1 (seq_len, then the table entries)
+  const UnitRange r = unit_range<B>(p, seq, split);
+#pragma unroll
+  for (int k = 0; k < NST; ++k) {
+    const int blk = (warp + k * W) * C::BPS + lane;
+    ph[k] = (lane < C::BPS && blk < r.nblk) ? __ldg(table + blk) : 0;
+  }
+#endif
   // a split without tokens has nothing to do -- unless its cluster waits for it at the merge barriers
   if (r.empty_split && !p.cluster_merge) return;
   const int nstages = r.nstages, nblk = r.nblk;
