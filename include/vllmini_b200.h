@@ -63,26 +63,24 @@ enum {
  *   max_seq_len upper bound on seq_lens[] (vllmini passes capacity, scheduler.py:97); used only
  *                to pick the split-KV factor -- a seq_lens[] entry above it is still attended in
  *                full (the last split runs to seq_len), so results never depend on the split
- *   workspace  optional device scratch for split-KV (arrival counters + fp32 partials), used only
- *                when the batch alone leaves SMs idle (num_seqs * num_heads <= #SMs and a long
- *                max_seq_len); may be NULL (=> never split).  16-byte aligned; must be zero-filled
- *                once before its first use; the kernel leaves it reusable.  The library keeps NO
- *                state of its own: the workspace is the caller's, and one workspace must not be
- *                shared by launches that can run concurrently (other streams) -- give each stream
- *                its own, as vllmini_b200/ops.py and csrc/torch_shim.cpp do.  Size from
- *                vb200_paged_attention_v1_workspace_bytes() (0 when this shape never splits).
  *   device     CUDA device ordinal the pointers live on (reference: OptionalCUDAGuard, :736)
  *   stream     cudaStream_t (reference: at::cuda::getCurrentCUDAStream(), :737)
  *
  * seq_lens[s] == 0 yields zeros for that row, as in the reference.  Entries of block_tables
  * at or beyond ceil(seq_len/block_size) are never read (attention_kernels.cu:227).
+ *
+ * Like the reference's v1 (SURVEY.md 8b "ownership"), the call needs no workspace and keeps no
+ * state: when the batch alone leaves SMs idle (num_seqs * num_heads <= #SMs, long max_seq_len)
+ * the context is split over up to 16 CTAs that form one thread-block cluster per (sequence,
+ * head) and merge their partial results through distributed shared memory inside the launch.
+ * Any number of calls may run concurrently on different streams.
  */
 int vb200_paged_attention_v1_f16(void* out, const void* query, const void* key_cache, const void* value_cache,
                                  const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
                                  int32_t num_heads, int32_t num_kv_heads, int32_t head_size, int32_t block_size,
                                  int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
-                                 int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
-                                 size_t workspace_bytes, int32_t device, void* stream);
+                                 int64_t kv_block_stride, int64_t kv_head_stride, float scale, int32_t device,
+                                 void* stream);
 
 /*
  * Fused decode step of one layer (no reference counterpart -- the reference
@@ -99,12 +97,7 @@ int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void
                                         int32_t block_size, int32_t max_num_blocks_per_seq, int32_t max_seq_len,
                                         int64_t q_stride, int64_t key_stride, int64_t value_stride,
                                         int64_t kv_block_stride, int64_t kv_head_stride, float scale,
-                                        void* workspace, size_t workspace_bytes, int32_t device, void* stream);
-
-/* Bytes of workspace that lets the launcher use its preferred split-KV factor for this problem shape
- * (64 KiB of arrival counters + the fp32 partials); 0 when the launcher would not split this shape. */
-size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
-                                                int32_t block_size, int32_t max_seq_len);
+                                        int32_t device, void* stream);
 
 /*
  * paged_attention_v2, fp16: the reference's partitioned entry (paged_attention_cuda.cpp:27-48; host entry
@@ -118,7 +111,7 @@ size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_he
  * partition kernel writes (:349-357, :484-495): the partition's max logit (scale * q.k, natural-log units), the
  * sum of exp(logit - max) and the partition's own normalised softmax(QK^T)V; partitions beyond a sequence's
  * length are left untouched, as in the reference (:119-122).  A second launch reduces the records into `out`
- * (:637-668; one live partition is copied, :580-592).  No other scratch: no workspace argument, no state.
+ * (:637-668; one live partition is copied, :580-592).  No other scratch, no state.
  */
 int vb200_paged_attention_v2_f16(void* out, float* exp_sums, float* max_logits, void* tmp_out, const void* query,
                                  const void* key_cache, const void* value_cache, const int32_t* block_tables,
@@ -194,10 +187,6 @@ int vb200_add_layernorm_f16(void* x_out, void* ln_out, const void* a, const int6
  * first index among equal maxima, NaN counts as the maximum (torch.argmax semantics). */
 int vb200_argmax_rows_f16(int64_t* out, const void* x, int64_t row_stride, int32_t num_rows, int32_t n,
                           int32_t device, void* stream);
-
-/* 0 when `stream` is not being captured into a CUDA graph, otherwise a non-zero id unique to that capture.  For
- * bindings that hand out split-KV workspaces: one per (device, stream, capture) keeps concurrent launches apart. */
-uint64_t vb200_stream_capture_id(void* stream);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* vb200_last_error(void);

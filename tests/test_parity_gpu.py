@@ -180,10 +180,11 @@ def _tiny_reshape_args():
     return k, k.clone(), kc, vc, torch.zeros(1, dtype=torch.int64, device=dev), "auto", 1.0
 
 
-def test_two_streams_splitting_concurrently_do_not_share_a_workspace():
+def test_two_streams_splitting_concurrently():
     """Two small-batch, long-context calls (both split-KV) issued on two streams so that they overlap on the GPU.
-    The C ABI keeps no state and the binding hands each stream its own scratch, so both results must be right --
-    with one shared workspace the arrival counters and partials of the two launches would collide."""
+    The library keeps no state and needs no workspace (the splits merge inside their thread-block cluster), so --
+    like the reference's v1 -- concurrent launches cannot disturb each other.  (Round 1's shared per-device
+    workspace would have let the arrival counters and partials of the two launches collide.)"""
     from vllmini_b200 import ops
     dev = torch.device("cuda:0")
     cases = []
@@ -216,7 +217,6 @@ def test_small_batch_long_context_uses_split_kv():
     c = dict(S=2, H=12, D=64, B=16, q=q, kc=kc, vc=vc, bt=bt, sl=sl, scale=0.125)
     from vllmini_b200 import _native
     assert "grid=(12,2,11)" in _native.plan(2, 12, 12, 64, 16, int(bt.shape[1]) * 16)             # 11 splits, one cluster each
-    assert _native.load().vb200_paged_attention_v1_workspace_bytes(2, 12, 64, 16, int(bt.shape[1]) * 16) == 0
     got = run_cuda_attention(c)
     truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, mode="exact").astype(np.float64)
     assert_close_to_truth(got, truth, what="split-KV")
@@ -842,25 +842,3 @@ def test_grouped_query_kernel_is_bit_identical_to_the_per_head_grid(D, B, KVH, r
     ops.paged_attention_v1_append(out_b, t[0], k_new, v_new, kc_b, vc_b, slots, KVH, 0.11, t[3], sl1, B, msl)
     torch.cuda.synchronize()
     assert torch.equal(kc_a, kc_b) and torch.equal(vc_a, vc_b) and torch.equal(out_a, out_b)
-
-
-def test_grouped_query_kernel_split_kv():
-    """The one batch size where the grouped-query kernel also splits the context: 4 units per SM of query heads
-    (592 = 74 x 8) is exactly one CTA per SM once 4 heads share a CTA, so the launcher halves the context."""
-    from vllmini_b200 import _native, ops
-    S, H, KVH, D, B = 74, 8, 2, 64, 16
-    rng = np.random.default_rng(5)
-    lens = rng.integers(1, 700, size=S).astype(np.int32)
-    q, kc, vc, bt, sl = po.make_case(S, KVH, D, B, lens, seed=9, max_blocks_per_seq=48)
-    q = rng.standard_normal((S, H, D)).astype(np.float16)
-    msl = 48 * B
-    plan = _native.plan(S, H, KVH, D, B, msl)
-    assert "pa_v1_gqa_kernel" in plan and "grid=(2,74,2)" in plan, plan
-    dev = torch.device("cuda:0")
-    t = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (q, kc, vc, bt, sl)]
-    out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
-    for _ in range(2):
-        ops.paged_attention_v1(out, t[0], t[1], t[2], KVH, 0.125, t[3], t[4], B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
-    torch.cuda.synchronize()
-    truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, num_kv_heads=KVH, mode="exact").astype(np.float64)
-    assert_close_to_truth(out.cpu().numpy(), truth, atol=1.5e-3, what="grouped-query kernel, split-KV")

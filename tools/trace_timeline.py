@@ -21,7 +21,7 @@ from sweep import CONFIGS, make  # noqa: E402
 lib = ctypes.CDLL(os.environ.get("VB200_TRACE_LIB") or
                   os.path.join(ROOT, "vllmini_b200", "lib", "trace", "libvllmini_b200.so"))
 vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
-lib.vb200_paged_attention_v1_f16.argtypes = [vp] * 6 + [i32] * 7 + [i64] * 3 + [f32, vp, sz, i32, vp]
+lib.vb200_paged_attention_v1_f16.argtypes = [vp] * 6 + [i32] * 7 + [i64] * 3 + [f32, i32, vp]
 lib.vb200_debug_set_trace.argtypes = [vp]
 lib.vb200_set_pdl.argtypes = [i32]
 
@@ -34,7 +34,6 @@ def run(name):
     pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(2)]
     nctas = S * H * 16          # room for a split launch (grid.z <= 16)
     trace = torch.zeros(nctas * 4, dtype=torch.int64, device=dev)
-    ws = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def call(i, tr):
@@ -43,7 +42,7 @@ def run(name):
         lib.vb200_debug_set_trace(tr)
         rc = lib.vb200_paged_attention_v1_f16(out.data_ptr(), q.data_ptr(), kc.data_ptr(), vc.data_ptr(), bt.data_ptr(),
                                               sl.data_ptr(), S, H, H, D, B, bt.shape[1], ctx, q.stride(0), kc.stride(0),
-                                              kc.stride(1), D ** -0.5, ws.data_ptr(), ws.numel(), 0, stream)
+                                              kc.stride(1), D ** -0.5, 0, stream)
         assert rc == 0
     for i in range(4):
         call(i, None)

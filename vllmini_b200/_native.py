@@ -20,11 +20,9 @@ ABI_VERSION = 2
 _vp, _i32, _i64, _f32, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
 SYMBOLS = {
     "vb200_paged_attention_v1_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
-                                            _i64, _i64, _i64, _f32, _vp, _sz, _i32, _vp]),
+                                            _i64, _i64, _i64, _f32, _i32, _vp]),
     "vb200_paged_attention_v1_append_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
-                                                   _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _sz,
-                                                   _i32, _vp]),
-    "vb200_paged_attention_v1_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+                                                   _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp]),
     "vb200_reshape_and_cache_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64,
                                            _i32, _vp]),
     "vb200_copy_blocks": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _vp]),
@@ -37,7 +35,6 @@ SYMBOLS = {
     "vb200_add_layernorm_f16": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _f32,
                                        _i32, _vp]),
     "vb200_argmax_rows_f16": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
-    "vb200_stream_capture_id": (ctypes.c_uint64, [_vp]),
     "vb200_last_error": (ctypes.c_char_p, []),
     "vb200_abi_version": (_i32, []),
     "vb200_launch_count": (ctypes.c_uint64, []),
@@ -115,8 +112,8 @@ def set_tuning(force_num_splits: int = 0, variant: int = 0) -> int:
 
 
 def set_merge(merge_mode: int = 0, max_cluster: int = 16) -> None:
-    """Experiments build only: split-KV merge through the thread-block cluster (0, shipped) or through round 1's
-    workspace + last-arriver path (1); cap on the cluster size."""
+    """Experiments build only: cap on the split-KV cluster size (merge_mode is ignored: round 1's workspace merge
+    was measured against the cluster merge, profiles/r02c_split_merge.md, and removed)."""
     lib = load()
     if not has_experiments():
         raise RuntimeError("vllmini_b200: this build has no sweep knobs (see set_tuning)")

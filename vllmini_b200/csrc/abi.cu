@@ -44,13 +44,3 @@ extern "C" int32_t vb200_set_pdl(int32_t enable) {
 }
 extern "C" uint64_t vb200_launch_count(void) { return vb200::g_launches.load(std::memory_order_relaxed); }
 
-// 0 when `stream` is not being captured into a CUDA graph, otherwise the capture's unique id (never 0).
-extern "C" uint64_t vb200_stream_capture_id(void* stream) {
-  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
-  unsigned long long id = 0;
-  if (cudaStreamGetCaptureInfo(static_cast<cudaStream_t>(stream), &status, &id) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return status == cudaStreamCaptureStatusActive ? (uint64_t)id + 1 : 0;
-}

@@ -196,103 +196,6 @@ __global__ void __launch_bounds__(128) reshape_and_cache_warp_kernel(
   }
 }
 
-// One CTA per (TT-token tile, head), one WARP per token: the rows are loaded exactly like the warp kernel does (slot
-// and row words in flight together, lanes <-> 32-bit words), the slots are exchanged through shared memory and the
-// tile is classified:
-//  * scattered slots (decode): the rows go straight from registers to the caches -- the warp kernel's stores, at
-//    the price of one CTA barrier;
-//  * consecutive slots (prefill): the rows are parked in shared memory and stored lane <-> token, so that one store
-//    instruction covers consecutive slots and the V-cache writes land as whole sectors (the tile kernel's phase 2).
-// One memory round trip in front of the stores in both cases.
-template <int TT>
-__global__ void __launch_bounds__(TT * 32) reshape_and_cache_rows_kernel(
-    const __half* __restrict__ key, const __half* __restrict__ value, __half* __restrict__ key_cache,
-    __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads,
-    int head_size, int block_size, int64_t key_stride, int64_t value_stride) {
-  extern __shared__ __align__(16) uint8_t tile_smem[];
-  __shared__ int64_t s_slot[32];
-  const int h = blockIdx.x;
-  const int t0 = blockIdx.y * TT;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  griddep_launch_dependents();  // PDL: see common.cuh
-  griddep_wait();
-  const int t = t0 + warp;
-  const bool live = t < num_tokens;
-  const int64_t my_slot = live ? slot_mapping[t] : -1;
-  constexpr int kMaxWords = 4;  // head_size <= 256
-  uint32_t kw[kMaxWords], vw[kMaxWords];
-  {
-    const uint32_t* krow = reinterpret_cast<const uint32_t*>(key + (int64_t)t * key_stride + (int64_t)h * head_size);
-    const uint32_t* vrow = reinterpret_cast<const uint32_t*>(value + (int64_t)t * value_stride + (int64_t)h * head_size);
-#pragma unroll
-    for (int u = 0; u < kMaxWords; ++u) {
-      const int i = lane + 32 * u;
-      if (live && i < head_size / 2) {
-        kw[u] = __ldg(krow + i);
-        vw[u] = __ldg(vrow + i);
-      }
-    }
-  }
-  if (lane == 0) s_slot[warp] = my_slot;
-  if (TT < 32 && threadIdx.x >= TT && threadIdx.x < 32) s_slot[threadIdx.x] = -1;
-  __syncthreads();
-  const int64_t slot = s_slot[lane];                       // lane <-> token of the tile (same in every warp)
-  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
-  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && lane < TT && slot >= 0 && slot == prev + 1);
-  const bool run_like = __popc(adj) >= TT / 2;
-
-  if (!run_like) {
-    if (my_slot < 0) return;  // padding token (cache_kernels.cu:166-169); also warps past num_tokens
-    const int64_t blk = my_slot / block_size;
-    const int off = (int)(my_slot % block_size);
-    uint32_t* kdst32 = reinterpret_cast<uint32_t*>(key_cache + (blk * num_heads + h) * (int64_t)head_size * block_size);
-    uint16_t* vdst =
-        reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
-#pragma unroll
-    for (int u = 0; u < kMaxWords; ++u) {
-      const int i = lane + 32 * u;  // 32-bit word i of the row: dims 2i, 2i+1
-      if (i < head_size / 2) {
-        kdst32[((int64_t)(i >> 2) * block_size + off) * 4 + (i & 3)] = kw[u];
-        vdst[(int64_t)(2 * i) * block_size] = (uint16_t)(vw[u] & 0xffffu);
-        vdst[(int64_t)(2 * i + 1) * block_size] = (uint16_t)(vw[u] >> 16);
-      }
-    }
-    return;
-  }
-
-  // ---- consecutive slots: park the rows, then lane <-> token ----
-  const int groups = head_size >> 3;
-  const int pitch = head_size * 2 + 16;     // K rows: 16-byte aligned, conflict-free for 128-bit column reads
-  const int vpitch = head_size / 2 + 1;     // V rows in 32-bit words, odd pitch: conflict-free column reads
-  uint8_t* ks = tile_smem;
-  uint32_t* vs = reinterpret_cast<uint32_t*>(tile_smem + TT * pitch);
-#pragma unroll
-  for (int u = 0; u < kMaxWords; ++u) {
-    const int i = lane + 32 * u;
-    if (live && i < head_size / 2) {
-      reinterpret_cast<uint32_t*>(ks + warp * pitch)[i] = kw[u];
-      vs[warp * vpitch + i] = vw[u];
-    }
-  }
-  __syncthreads();
-  if (lane >= TT || slot < 0) return;
-  const int64_t blk = slot / block_size;
-  const int off = (int)(slot % block_size);
-  __half* kdst = key_cache + ((blk * num_heads + h) * (int64_t)groups * block_size + off) * 8;
-  for (int g = warp; g < groups; g += TT)
-    *reinterpret_cast<uint4*>(kdst + (int64_t)g * block_size * 8) =
-        *reinterpret_cast<const uint4*>(ks + lane * pitch + g * 16);
-  uint16_t* vdst =
-      reinterpret_cast<uint16_t*>(value_cache) + (blk * num_heads + h) * (int64_t)head_size * block_size + off;
-  const uint32_t* vrow = vs + lane * vpitch;
-  for (int d2 = warp; d2 < head_size / 2; d2 += TT) {
-    const uint32_t w = vrow[d2];
-    vdst[(int64_t)(2 * d2) * block_size] = (uint16_t)(w & 0xffffu);
-    vdst[(int64_t)(2 * d2 + 1) * block_size] = (uint16_t)(w >> 16);
-  }
-}
-
 // any x / alignment: one thread per element, literal index formulas of cache_kernels.cu:178-199
 __global__ void __launch_bounds__(256) reshape_and_cache_generic_kernel(
     const uint16_t* __restrict__ key, const uint16_t* __restrict__ value, uint16_t* __restrict__ key_cache,
@@ -358,18 +261,6 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
                                      static_cast<const __half*>(key), static_cast<const __half*>(value),
                                      static_cast<__half*>(key_cache), static_cast<__half*>(value_cache), slot_mapping,
                                      num_tokens, num_heads, head_size, block_size, key_stride, value_stride));
-      count_launch();
-      return VB200_OK;
-    }
-    if (mode == 4 || mode == 5) {
-      const int tt = mode == 4 ? 16 : 32;
-      const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
-      dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
-      auto kern = tt == 16 ? reshape_and_cache_rows_kernel<16> : reshape_and_cache_rows_kernel<32>;
-      VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(tt * 32), (size_t)smem, s, static_cast<const __half*>(key),
-                                     static_cast<const __half*>(value), static_cast<__half*>(key_cache),
-                                     static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size,
-                                     block_size, key_stride, value_stride));
       count_launch();
       return VB200_OK;
     }

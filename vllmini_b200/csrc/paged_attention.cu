@@ -15,7 +15,8 @@
 //   fp16 p, fp16 PV partial sums                 no CTA barrier in the main loop
 //   no split-KV in v1                            fp16 p, exact fp16xfp16 products, fp32 accumulation
 //                                                (FHFMA = fma.rn.f32.f16, sm_100+)
-//                                                split-KV with an in-kernel last-arriver merge
+//                                                split-KV: the splits of a (seq, head) form a thread-block
+//                                                cluster and merge through distributed shared memory
 //
 // Layout facts used (vllmini/kv_cache.py:13-14): for one (physical block,
 // kv head) the K tile [D/8][B][8] and the V tile [D][B] are each D*B*2 contiguous bytes, so one
@@ -52,9 +53,6 @@ struct PaParams {
   int split_tokens;  // multiple of 32; ignored when num_splits == 1
   int cluster_merge; // != 0: the num_splits CTAs of a (seq, head) form one thread-block cluster (1, 1, num_splits) and
                      // merge their partials through distributed shared memory -- no workspace, no counters
-  int32_t* ws_cnt;   // [num_seqs * num_heads] zero between launches
-  float* ws_ml;      // [num_seqs * num_heads * num_splits * 2]
-  float* ws_o;       // [num_seqs * num_heads * num_splits * D]
   // fused append (vb200_paged_attention_v1_append_f16): this step's K/V rows [num_seqs, num_kv_heads, D] are
   // scattered into the caches by the CTA that attends over the new token.  new_k == nullptr: plain v1.
   const __half* __restrict__ new_k;
@@ -269,12 +267,12 @@ __device__ __forceinline__ void warp_publish(float* red, int warp, int lane, flo
   }
 }
 
-// CTA-level log-sum-exp merge of the W warps' partials (after a barrier), then either the final
-// normalised fp16 row (nsplit_seq == 1) or a split-KV partial + last-arriver merge.
-// `tid` in [0, W*32); BAR = named barrier id used by the W*32 compute threads.
-template <class C, int W, int BAR>
+// CTA-level log-sum-exp merge of the W warps' partials (after a barrier), then the final normalised fp16 row, the
+// paged_attention_v2 partition record, or -- split-KV -- the merge across the CTAs of the cluster.
+// `tid` in [0, W*32); `part`: (D + 2) floats of this CTA's shared memory, at the same offset in every CTA.
+template <class C, int W>
 __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const float* red, int tid, int seq, int head,
-                                                    int split, int nsplit_seq, int* s_last, float* part) {
+                                                    int split, int nsplit_seq, float* part) {
   constexpr int D = C::kD;
   float M = -INFINITY;
 #pragma unroll
@@ -360,50 +358,7 @@ __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const flo
     return;
   }
 
-  // ---- split-KV: publish the partial, last arriver of this (seq, head) merges ----
-  {
-    const int64_t part_idx = row * p.num_splits + split;
-    for (int d = tid; d < D; d += W * 32) {
-      float o = 0.f;
-#pragma unroll
-      for (int w = 0; w < W; ++w) o += red[w * (D + 2) + d] * wgt[w];
-      p.ws_o[part_idx * D + d] = o;
-    }
-    if (tid == 0) {
-      p.ws_ml[part_idx * 2] = M;
-      p.ws_ml[part_idx * 2 + 1] = L;
-    }
-  }
-  __threadfence();
-  named_bar_sync<BAR, W * 32>();
-  if (tid == 0) {
-    const int prev = atomicAdd(p.ws_cnt + row, 1);
-    *s_last = (prev == nsplit_seq - 1);
-    if (prev == nsplit_seq - 1) p.ws_cnt[row] = 0;  // leave the workspace reusable
-  }
-  named_bar_sync<BAR, W * 32>();
-  if (!*s_last) return;
-  __threadfence();
-  {
-    const float* ml = p.ws_ml + row * p.num_splits * 2;
-    float Mg = -INFINITY;
-    for (int i = 0; i < nsplit_seq; ++i) Mg = fmaxf(Mg, ld_cg_f32(ml + 2 * i));
-    float Lg = 0.f;
-    for (int i = 0; i < nsplit_seq; ++i) {
-      const float mi = ld_cg_f32(ml + 2 * i);
-      Lg += ld_cg_f32(ml + 2 * i + 1) * ((mi == -INFINITY) ? 0.f : ex2(mi - Mg));
-    }
-    const float inv = __fdividef(1.f, Lg + 1e-6f);
-    for (int d = tid; d < D; d += W * 32) {
-      float o = 0.f;
-      for (int i = 0; i < nsplit_seq; ++i) {
-        const float mi = ld_cg_f32(ml + 2 * i);
-        const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
-        o += ld_cg_f32(p.ws_o + (row * p.num_splits + i) * D + d) * wi;
-      }
-      p.out[row * D + d] = __float2half_rn(o * inv);
-    }
-  }
+  // (a split launch always runs as a cluster: nsplit_seq > 1 without cluster_merge does not occur)
 }
 
 // Token range of (seq, split) and derived counts.
@@ -444,7 +399,6 @@ template <int D, int B, int W, int NST, bool APPEND>
 __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   using C = PaCfg<D, B, W, NST>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_last;
 
   const int head = blockIdx.x;
   const int seq = blockIdx.y;
@@ -467,32 +421,13 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   }
   griddep_wait();
 
-  // The table entries of this warp's first ring do not depend on seq_len: fetch them together with it (one
-  // dependent memory round trip less in front of the first bulk copy).  Reading inside the table row is always
-  // safe; entries beyond the sequence's blocks are fetched but never used.
-  const int blk_begin = (p.num_splits > 1 || p.v2_exp_sums != nullptr) ? split * (p.split_tokens / B) : 0;
-  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + blk_begin;
-  int ph[NST];
-#ifndef VB200_NO_SPEC_TABLE
-#pragma unroll
-  for (int k = 0; k < NST; ++k) {
-    const int blk = (warp + k * W) * C::BPS + lane;
-    ph[k] = (lane < C::BPS && blk_begin + blk < p.max_blocks_per_seq) ? __ldg(table + blk) : 0;
-  }
   const UnitRange r = unit_range<B>(p, seq, split);
-#else   // A/B builds only: the dependent order of round 1 (seq_len, then the table entries)
-  const UnitRange r = unit_range<B>(p, seq, split);
-#pragma unroll
-  for (int k = 0; k < NST; ++k) {
-    const int blk = (warp + k * W) * C::BPS + lane;
-    ph[k] = (lane < C::BPS && blk < r.nblk) ? __ldg(table + blk) : 0;
-  }
-#endif
   // a split without tokens has nothing to do -- unless its cluster waits for it at the merge barriers
   if (r.empty_split && !p.cluster_merge) return;
   const int nstages = r.nstages, nblk = r.nblk;
 
   const int kv_head = head / (p.num_heads / p.num_kv_heads);
+  const int32_t* table = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + r.tok_begin / B;
   const __half* kbase = p.kc + (int64_t)kv_head * p.kv_head_stride;
   const __half* vbase = p.vc + (int64_t)kv_head * p.kv_head_stride;
 
@@ -538,10 +473,17 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
     return (lane < C::BPS && blk < nblk) ? __ldg(table + blk) : 0;
   };
 
-  // prologue: fill the ring (table entries prefetched above)
+  // prologue: fill the ring.  (Fetching these table entries speculatively, together with seq_len, was measured
+  // twice -- profiles/r01i_cta_timeline.md, profiles/r02d_spec_table_prefetch.md -- and gains nothing: both loads
+  // are L2 hits, the wait for the first stage is HBM queueing.)
+  {
+    int ph[NST];
 #pragma unroll
-  for (int k = 0; k < NST; ++k)
-    if (warp + k * W < nstages) issue_stage(warp + k * W, k, ph[k]);
+    for (int k = 0; k < NST; ++k) ph[k] = (warp + k * W < nstages) ? load_phys(warp + k * W) : 0;
+#pragma unroll
+    for (int k = 0; k < NST; ++k)
+      if (warp + k * W < nstages) issue_stage(warp + k * W, k, ph[k]);
+  }
   int next_phys = (warp + NST * W < nstages) ? load_phys(warp + NST * W) : 0;
 
   // ---- q: dims 8*(lane/B + j*BPS) .. +7 of this head's row, packed fp16 ----
@@ -622,8 +564,7 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   float* red = reinterpret_cast<float*>(smem + C::RED_OFF);  // [W][D + 2]
   warp_publish<C>(red, warp, lane, m, lsum, acc);
   __syncthreads();
-  cta_merge_and_store<C, W, 1>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, &s_last,
-                               reinterpret_cast<float*>(smem));
+  cta_merge_and_store<C, W>(p, red, threadIdx.x, seq, head, split, r.nsplit_seq, reinterpret_cast<float*>(smem));
 #ifdef VB200_TRACE
   if (threadIdx.x == 0 && p.trace != nullptr) {
     unsigned long long t_end;
@@ -763,7 +704,6 @@ template <int D, int B, int W, int NST, bool APPEND, int G>
 __global__ void __launch_bounds__(W * 32, PaCfgG<D, B, W, NST, G>::CTAS_PER_SM) pa_v1_gqa_kernel(const PaParams p) {
   using C = PaCfgG<D, B, W, NST, G>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int s_last;
 
   const int head0 = blockIdx.x * G;  // first of this CTA's G query heads (all of one kv head)
   const int seq = blockIdx.y;
@@ -902,8 +842,8 @@ __global__ void __launch_bounds__(W * 32, PaCfgG<D, B, W, NST, G>::CTAS_PER_SM) 
   for (int g = 0; g < G; ++g) warp_publish<C>(red + g * (W * (D + 2)), warp, lane, m[g], lsum[g], acc[g]);
   __syncthreads();
   for (int g = 0; g < G; ++g)
-    cta_merge_and_store<C, W, 1>(p, red + g * (W * (D + 2)), threadIdx.x, seq, head0 + g, split, r.nsplit_seq, &s_last,
-                                 reinterpret_cast<float*>(smem));
+    cta_merge_and_store<C, W>(p, red + g * (W * (D + 2)), threadIdx.x, seq, head0 + g, split, r.nsplit_seq,
+                              reinterpret_cast<float*>(smem));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -951,7 +891,6 @@ __global__ void __launch_bounds__(128) pa_v2_reduce_kernel(__half* __restrict__ 
 // --------------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------------
-constexpr int kCounterCap = 16384;     // int32 split-KV arrival counters at the start of the workspace (one per row)
 constexpr int kV2PartitionTokens = 512;  // PARTITION_SIZE of the reference's v2 launcher (attention_kernels.cu:847)
 
 #ifdef VB200_TRACE
@@ -969,8 +908,7 @@ struct Shape {
 struct Tuning {
   int force_splits = 0;
   int variant = 0;
-  int merge_mode = 0;    // 0: cluster merge (shipped behaviour), 1: workspace + last-arriver merge (round-1 path)
-  int max_cluster = 16;  // cap on the cluster size / split factor of the cluster merge
+  int max_cluster = 16;  // cap on the cluster size / split factor
 };
 static Tuning g_tuning;
 // 0: default; 1: 4x3; 2: 8x1; 3: 2x2; 4: default kernel with the grouped-query path off
@@ -978,12 +916,10 @@ static constexpr Shape kVariants[] = {{0, 2}, {4, 3}, {8, 1}, {2, 2}, {0, 2}};
 constexpr int kNumVariants = 5;
 static int tuning_variant() { return g_tuning.variant; }
 static int tuning_force_splits() { return g_tuning.force_splits; }
-static int tuning_merge_mode() { return g_tuning.merge_mode; }
 static int tuning_max_cluster() { return g_tuning.max_cluster; }
 #else
 static constexpr int tuning_variant() { return 0; }
 static constexpr int tuning_force_splits() { return 0; }
-static constexpr int tuning_merge_mode() { return 0; }
 static constexpr int tuning_max_cluster() { return 16; }
 #endif
 
@@ -1228,27 +1164,9 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
   *split_tokens = st;
 }
 
-// workspace = [kCounterCap int32 split counters][ml: rows*2 f32][o: rows*D f32]; nothing when the launch is not split
-static size_t workspace_bytes_for(int num_seqs, int num_heads, int head_size, int num_splits) {
-  if (num_splits <= 1) return 0;
-  const size_t rows = (size_t)num_seqs * num_heads * num_splits;
-  return (size_t)kCounterCap * 4 + rows * 2 * 4 + rows * head_size * 4;
-}
-
 }  // namespace vb200
 
 using namespace vb200;
-
-extern "C" size_t vb200_paged_attention_v1_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_size,
-                                                           int32_t block_size, int32_t max_seq_len) {
-  (void)block_size;
-  if (num_seqs <= 0 || num_heads <= 0 || !head_size_supported(head_size)) return 0;
-  if (tuning_merge_mode() == 0) return 0;   // split-KV merges inside a thread-block cluster: no scratch at all
-  int ns = 1, st = 0;
-  choose_split(num_seqs, num_heads, head_size, max_seq_len, tuning_variant(), device_sm_count(), 1, 64, &ns, &st);
-  if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;   // one counter per (sequence, query head) row
-  return workspace_bytes_for(num_seqs, num_heads, head_size, ns);
-}
 
 namespace {
 struct ExtraArgs {
@@ -1270,8 +1188,8 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
                                 const int32_t* block_tables, const int32_t* seq_lens, int32_t num_seqs,
                                 int32_t num_heads, int32_t num_kv_heads, int32_t head_size, int32_t block_size,
                                 int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
-                                int64_t kv_block_stride, int64_t kv_head_stride, float scale, void* workspace,
-                                size_t workspace_bytes, int32_t device, void* stream, const ExtraArgs& a) {
+                                int64_t kv_block_stride, int64_t kv_head_stride, float scale, int32_t device,
+                                void* stream, const ExtraArgs& a) {
   const bool planning = a.plan != nullptr;
   const bool v2 = a.v2_exp_sums != nullptr;
   if (num_seqs < 0 || num_heads <= 0 || num_kv_heads <= 0 || max_num_blocks_per_seq < 0)
@@ -1328,26 +1246,15 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     ns = (max_seq_len + st - 1) / st;
     if (ns < 1) ns = 1;
     if (ns > 65535) return set_error(VB200_ERR_INVALID_ARGUMENT, "max_seq_len %d exceeds grid.z limit", max_seq_len);
-  } else if (group == 1 && max_seq_len > 0 && tuning_merge_mode() == 0) {
+  } else if (group == 1 && max_seq_len > 0) {
     // split-KV, merged inside a thread-block cluster of the splits of a (sequence, head): no scratch, no state
     int cap = planning ? 16 : cluster_cap_for(head_size);
     if (cap > tuning_max_cluster()) cap = tuning_max_cluster();
     choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, 1, cap, &ns, &st);
     p.cluster_merge = ns > 1;
-  } else if (group == 1 && max_seq_len > 0) {
-    // experiments build only: round 1's workspace + last-arriver merge, kept for A/B measurements
-    if (!planning && workspace != nullptr && (((uintptr_t)workspace & 15) || workspace_bytes < (size_t)kCounterCap * 4))
-      workspace = nullptr;  // unusable scratch: run without split
-    if (planning || workspace != nullptr)
-      choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, 1, 64, &ns, &st);
-    if ((int64_t)num_seqs * num_heads > kCounterCap) ns = 1;
-    if (!planning && ns > 1 && workspace_bytes_for(num_seqs, num_heads, head_size, ns) > workspace_bytes) ns = 1;
   }
   p.num_splits = ns;
   p.split_tokens = st;
-  p.ws_cnt = nullptr;
-  p.ws_ml = nullptr;
-  p.ws_o = nullptr;
   p.new_k = static_cast<const __half*>(a.new_k);
   p.new_v = static_cast<const __half*>(a.new_v);
   p.slot_mapping = a.slot_mapping;
@@ -1361,12 +1268,6 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
 #ifdef VB200_TRACE
   p.trace = g_trace;
 #endif
-  if (ns > 1 && !v2 && !planning) {
-    const size_t rows = (size_t)num_seqs * num_heads * ns;
-    p.ws_cnt = static_cast<int32_t*>(workspace);
-    p.ws_ml = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (size_t)kCounterCap * 4);
-    p.ws_o = p.ws_ml + rows * 2;
-  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (group > 1) {
     // grouped-query shapes, batch large enough to be bandwidth-bound: share each landed tile among the group
@@ -1415,11 +1316,10 @@ extern "C" int vb200_paged_attention_v1_f16(void* out, const void* query, const 
                                             int32_t num_kv_heads, int32_t head_size, int32_t block_size,
                                             int32_t max_num_blocks_per_seq, int32_t max_seq_len, int64_t q_stride,
                                             int64_t kv_block_stride, int64_t kv_head_stride, float scale,
-                                            void* workspace, size_t workspace_bytes, int32_t device, void* stream) {
+                                            int32_t device, void* stream) {
   return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
                               num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
-                              kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream,
-                              ExtraArgs{});
+                              kv_block_stride, kv_head_stride, scale, device, stream, ExtraArgs{});
 }
 
 extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query, const void* key, const void* value,
@@ -1430,8 +1330,7 @@ extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query,
                                                    int32_t max_num_blocks_per_seq, int32_t max_seq_len,
                                                    int64_t q_stride, int64_t key_stride, int64_t value_stride,
                                                    int64_t kv_block_stride, int64_t kv_head_stride, float scale,
-                                                   void* workspace, size_t workspace_bytes, int32_t device,
-                                                   void* stream) {
+                                                   int32_t device, void* stream) {
   if (num_seqs > 0 && (!key || !value || !slot_mapping))
     return set_error(VB200_ERR_INVALID_ARGUMENT, "null pointer argument");
   if ((((uintptr_t)key | (uintptr_t)value) & 15) || (key_stride % 8) || (value_stride % 8))
@@ -1444,7 +1343,7 @@ extern "C" int vb200_paged_attention_v1_append_f16(void* out, const void* query,
   a.new_v_stride = value_stride;
   return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
                               num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
-                              kv_block_stride, kv_head_stride, scale, workspace, workspace_bytes, device, stream, a);
+                              kv_block_stride, kv_head_stride, scale, device, stream, a);
 }
 
 extern "C" int vb200_paged_attention_v2_f16(void* out, float* exp_sums, float* max_logits, void* tmp_out,
@@ -1463,7 +1362,7 @@ extern "C" int vb200_paged_attention_v2_f16(void* out, float* exp_sums, float* m
   a.v2_tmp_out = tmp_out;
   return paged_attention_impl(out, query, key_cache, value_cache, block_tables, seq_lens, num_seqs, num_heads,
                               num_kv_heads, head_size, block_size, max_num_blocks_per_seq, max_seq_len, q_stride,
-                              kv_block_stride, kv_head_stride, scale, nullptr, 0, device, stream, a);
+                              kv_block_stride, kv_head_stride, scale, device, stream, a);
 }
 
 extern "C" int vb200_paged_attention_plan(char* buf, size_t buf_bytes, int32_t num_seqs, int32_t num_heads,
@@ -1477,8 +1376,7 @@ extern "C" int vb200_paged_attention_plan(char* buf, size_t buf_bytes, int32_t n
   static const int dummy = 0;
   if (fused_append) a.new_k = &dummy;   // selects the APPEND instantiation; never dereferenced while planning
   const int rc = paged_attention_impl(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, num_seqs, num_heads,
-                                      num_kv_heads, head_size, block_size, 0, max_seq_len, 0, 0, 0, 1.f, nullptr, 0,
-                                      -1, nullptr, a);
+                                      num_kv_heads, head_size, block_size, 0, max_seq_len, 0, 0, 0, 1.f, -1, nullptr, a);
   if (rc != VB200_OK) return rc;
   if (plan.G > 1)
     snprintf(buf, buf_bytes, "vb200::%s<%d,%d,%d,%d,%d,%d> grid=(%u,%u,%u) block=%d smem=%d", plan.kernel, plan.D,
@@ -1497,9 +1395,10 @@ extern "C" int32_t vb200_debug_set_tuning(int32_t force_num_splits, int32_t vari
   g_tuning.variant = (variant < 0 || variant >= kNumVariants) ? 0 : variant;
   return prev;
 }
-// merge_mode 0: cluster merge, 1: round 1's workspace merge; max_cluster: cap on the cluster size (2..16)
+// cap on the cluster size = split factor (2..16); merge_mode is accepted for old sweep scripts and ignored (round 1's
+// workspace merge was measured against the cluster merge in profiles/r02c_split_merge.md and removed)
 extern "C" void vb200_debug_set_merge(int32_t merge_mode, int32_t max_cluster) {
-  g_tuning.merge_mode = merge_mode ? 1 : 0;
+  (void)merge_mode;
   g_tuning.max_cluster = max_cluster < 1 ? 16 : max_cluster;
 }
 #endif

@@ -4,57 +4,24 @@
 // paged_attention_cuda.cpp:51-61) whose functions take torch::Tensor& positionally.  This file is the same
 // layer for the B200 path: it only validates arguments (mirroring the reference's TORCH_CHECKs and
 // data_ptr<T>() dtype checks), extracts pointers / strides / the current CUDA stream, and calls the
-// extern "C" entry points of libvllmini_b200.so.  No kernel, no arithmetic and no allocation visible to the
-// caller lives here.  The C ABI keeps no state; the split-KV scratch it may be handed is owned by this binding:
-// one zero-filled tensor per (device, stream, graph capture), so launches that can run concurrently never share
-// one (the reference's v1 has no such scratch and is stream-safe; so is this).
+// extern "C" entry points of libvllmini_b200.so.  No kernel, no arithmetic, no allocation and no state lives
+// here (nor below: the library has no workspace -- split-KV merges inside a thread-block cluster -- so, like the
+// reference's v1, any number of calls may be in flight on different streams).
 // vllmini_b200/ops.py falls back to an equivalent ctypes path when this module is not built; both end in the
 // same C ABI and the same kernels.
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
-#include <map>
-#include <mutex>
 #include <string>
-#include <tuple>
-#include <vector>
 
 #include "vllmini_b200.h"
 
 namespace {
 
-// Workspace tensors keyed by (device, stream handle, capture id; 0 = not capturing).  Launches on one stream are
-// ordered and may share a workspace; a graph under capture gets its own (allocated from the graph's private pool,
-// its zero fill becomes a memset node).  Nothing is ever freed -- an outgrown buffer moves to `retired` because a
-// captured graph or an in-flight launch may still hold its raw pointer -- and the containers are deliberately
-// leaked: a static at::Tensor would be destroyed at interpreter exit, possibly after torch's CUDA allocator.
-using WsKey = std::tuple<int, uintptr_t, uint64_t>;
-struct WsPool {
-  std::mutex mu;
-  std::map<WsKey, at::Tensor> live;
-  std::vector<at::Tensor> retired;
-};
-WsPool* const g_ws = new WsPool;
-
 void check_rc(int rc) {
   // reference: TORCH_CHECK -> c10::Error -> Python RuntimeError
   TORCH_CHECK(rc == 0, "vllmini_b200: ", vb200_last_error(), " (code ", rc, ")");
-}
-
-void* workspace_for(const at::Tensor& like, cudaStream_t stream, size_t bytes, size_t* got) {
-  *got = 0;
-  if (bytes == 0) return nullptr;   // this shape never splits: no scratch, nothing shared
-  const WsKey key{like.get_device(), (uintptr_t)stream, vb200_stream_capture_id((void*)stream)};
-  std::lock_guard<std::mutex> lock(g_ws->mu);
-  at::Tensor& ws = g_ws->live[key];
-  if (!ws.defined() || (size_t)ws.numel() < bytes) {
-    if (ws.defined()) g_ws->retired.push_back(ws);
-    const int64_t n = (int64_t)std::max<size_t>(bytes, (size_t)1 << 20);
-    ws = at::zeros({n}, like.options().dtype(at::kByte));   // on the current stream == `stream`
-  }
-  *got = (size_t)ws.numel();
-  return ws.data_ptr();
 }
 
 void paged_attention_v1(at::Tensor& out, at::Tensor& query, at::Tensor& key_cache, at::Tensor& value_cache,
@@ -91,17 +58,11 @@ void paged_attention_v1(at::Tensor& out, at::Tensor& query, at::Tensor& key_cach
   const int dev = query.get_device();
   const c10::cuda::CUDAGuard device_guard((c10::DeviceIndex)dev);   // reference: OptionalCUDAGuard(device_of(query))
   cudaStream_t stream = c10::cuda::getCurrentCUDAStream(dev).stream();
-  size_t ws_bytes = 0;
-  void* ws = workspace_for(query, stream,
-                           vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size,
-                                                                    (int)block_size, (int)max_seq_len),
-                           &ws_bytes);
   check_rc(vb200_paged_attention_v1_f16(out.data_ptr(), query.data_ptr(), key_cache.data_ptr(),
                                         value_cache.data_ptr(), block_tables.data_ptr<int>(),
                                         seq_lens.data_ptr<int>(), num_seqs, num_heads, (int)num_kv_heads, head_size,
                                         (int)block_size, max_blocks, (int)max_seq_len, query.stride(0),
-                                        key_cache.stride(0), key_cache.stride(1), (float)scale, ws, ws_bytes, dev,
-                                        (void*)stream));
+                                        key_cache.stride(0), key_cache.stride(1), (float)scale, dev, (void*)stream));
 }
 
 void reshape_and_cache(at::Tensor& key, at::Tensor& value, at::Tensor& key_cache, at::Tensor& value_cache,

@@ -7,12 +7,13 @@ the C ABI in include/vllmini_b200.h: this file only extracts pointers, sizes, st
 current CUDA stream from torch tensors.  PyTorch is plumbing here (device memory + streams).
 
 Like the reference, every call is asynchronous on torch's current stream of the tensors' device,
-allocates nothing the caller can see, and returns None.
+allocates nothing (there is no workspace: split-KV merges inside a thread-block cluster), keeps no
+state, and returns None.
 """
 from __future__ import annotations
 
 import os as _os
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 
@@ -20,15 +21,6 @@ from . import _native
 
 _ERR_NAMES = {-1: "CUDA error", -2: "Unsupported block size", -3: "Unsupported head size",
               -4: "invalid argument", -5: "unsupported"}
-
-# Split-KV scratch, one per (device, stream, capture): the C ABI keeps no state -- the workspace is the caller's
-# (include/vllmini_b200.h) -- and this binding is that caller.  Launches on one stream are ordered, so they may share
-# a workspace; launches on different streams (or in different captured graphs, which may later be replayed
-# concurrently) get their own.  Zero-filled once, the kernel leaves it reusable.  Buffers are never freed: a
-# captured CUDA graph or an in-flight launch may still hold the raw pointer of one that was outgrown.
-_workspaces: Dict[tuple, torch.Tensor] = {}
-_retired_workspaces: List[torch.Tensor] = []
-
 
 def _check(rc: int) -> None:
     if rc != 0:
@@ -40,23 +32,6 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         # reference: "CUDAGuardImpl initialized with non-CUDA DeviceType: cpu" 
         raise RuntimeError(f"vllmini_b200: {name} must be a CUDA tensor, got device {t.device}")
-
-
-def _workspace(device: torch.device, stream: int, nbytes: int) -> Optional[torch.Tensor]:
-    """Scratch for a split-KV launch on `stream` (a cudaStream_t handle); None when the shape never splits."""
-    if nbytes <= 0:
-        return None
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    # a graph under capture gets a workspace of its own (allocated from the graph's private pool, zero-filled by a
-    # captured memset node), so two captured graphs replayed concurrently never share one
-    key = (idx, int(stream), int(_native.load().vb200_stream_capture_id(stream)))
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        if ws is not None:
-            _retired_workspaces.append(ws)
-        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
 
 
 def paged_attention_v1(
@@ -120,16 +95,11 @@ def paged_attention_v1(
     dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     lib = _native.load()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
-                                                            int(max_seq_len))
-    ws = _workspace(dev, stream, ws_bytes)
     rc = lib.vb200_paged_attention_v1_f16(
         out.data_ptr(), query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
         block_tables.data_ptr(), seq_lens.data_ptr(),
         num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size), max_blocks, int(max_seq_len),
-        query.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
-        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
-        dev_index, stream)
+        query.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale), dev_index, stream)
     _check(rc)
 
 
@@ -215,16 +185,13 @@ def paged_attention_v1_append(
     dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
     lib = _native.load()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    ws_bytes = lib.vb200_paged_attention_v1_workspace_bytes(num_seqs, num_heads, head_size, int(block_size),
-                                                            int(max_seq_len))
-    ws = _workspace(dev, stream, ws_bytes)
     rc = lib.vb200_paged_attention_v1_append_f16(
         out.data_ptr(), query.data_ptr(), key.data_ptr(), value.data_ptr(), key_cache.data_ptr(),
         value_cache.data_ptr(), slot_mapping.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
         num_seqs, num_heads, int(num_kv_heads), head_size, int(block_size),
         block_tables.size(1) if block_tables.dim() == 2 else 0, int(max_seq_len),
         query.stride(0), key.stride(0), value.stride(0), key_cache.stride(0), key_cache.stride(1), float(scale),
-        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, dev_index, stream)
+        dev_index, stream)
     _check(rc)
 
 
