@@ -240,3 +240,45 @@ def test_graphed_bucket_padded_prefill_equals_eager_prefill():
     torch.cuda.synchronize()
     assert torch.equal(kv_e.key_cache, kv_g.key_cache) and torch.equal(kv_e.value_cache, kv_g.value_cache)
     assert np.array_equal(kv_e.h_tables, kv_g.h_tables)
+
+
+@pytest.mark.parametrize("name,graph_bucket", [("gpt2_greedy_tiny", 0), ("gpt2_greedy_tiny", 16), ("gpt2_greedy_small", 0)])
+def test_prefill_through_the_paged_path(name, graph_bucket):
+    """prefill_attention="paged" runs the prompt's causal attention through
+    paged_attention_v1 itself -- one row per prompt token, all rows sharing the sequence's block table, row t with
+    seq_len t + 1, K/V read back from the cache reshape_and_cache just filled.  It must agree with the library-kernel
+    prefill (same caches bit for bit in layer 0, last-position logits within fp16 noise, same greedy token), with
+    the reference model's golden logits, and the decode steps that follow must be unaffected."""
+    g, shape = _load(name)
+    dev = torch.device("cuda:0")
+    sd = synthetic_gpt2_state_dict(shape, seed=int(g["seed"]))
+    prompt = g["prompt"].tolist()
+
+    def run(mode):
+        model = GPT2Decoder(shape, dev, prefill_attention=mode)
+        model.load_state_dict(sd)
+        kv = BatchedKVState(shape.n_layer * 2 * 4, shape.n_layer, shape.n_head, shape.head_size, 16, 2, 4, dev)
+        other = np.random.default_rng(1).integers(0, shape.vocab_size, size=21).tolist()
+        model.prefill(torch.tensor(other, dtype=torch.int64, device=dev), kv, 0, graph_bucket=graph_bucket)
+        lg = model.prefill(torch.tensor(prompt, dtype=torch.int64, device=dev), kv, 1, graph_bucket=graph_bucket).clone()
+        toks = [int(lg.argmax())]
+        cur = torch.zeros(2, dtype=torch.int64, device=dev)
+        cur[1] = toks[0]
+        for _ in range(3):
+            kv.begin_decode_step(attend_to_new_token=True)
+            cur = model.greedy(model.decode_forward(cur, kv.d_pos, kv))
+            toks.append(int(cur[1]))
+        torch.cuda.synchronize()
+        return lg.float().cpu().numpy(), toks, kv
+
+    lg_s, toks_s, kv_s = run("sdpa")
+    lg_p, toks_p, kv_p = run("paged")
+    assert np.abs(lg_s - lg_p).max() < 2e-2
+    want_v, want_i = g["top_vals"][0], g["top_ids"][0]               # the reference model's own prefill logits
+    assert np.abs(lg_p[want_i] - want_v).max() < 0.06
+    if want_v[0] - want_v[1] > 0.12:
+        assert toks_p[0] == int(g["tokens"][0]) == toks_s[0]
+    blocks0 = torch.tensor(sorted(int(b) for b in kv_s.h_tables[0][kv_s.h_tables[0] >= 0]), device=dev)
+    assert np.array_equal(kv_s.h_tables, kv_p.h_tables)
+    assert torch.equal(kv_s.key_cache[blocks0], kv_p.key_cache[blocks0])      # layer 0: embeddings only
+    assert (kv_s.key_cache.float() - kv_p.key_cache.float()).abs().max().item() < 5e-2

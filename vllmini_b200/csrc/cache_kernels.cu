@@ -28,9 +28,8 @@ namespace vb200 {
 //    the layout dictates -- so the rows go straight from registers to the caches, warp <-> token, without the
 //    staging pass and its CTA barrier (the staged fallback of round 1 lost to the reference kernel here, 14.2 vs
 //    13.2 us at 2048 tokens).
-constexpr int kTileThreads = 128;
 
-template <int kTileTokens>   // 32, or 16 for small batches (more CTAs in flight)
+template <int kTileTokens, int kTileThreads, bool kEager = false>   // tokens: 32, or 16 for small batches
 __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
     const __half* __restrict__ key, const __half* __restrict__ value, __half* __restrict__ key_cache,
     __half* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads,
@@ -54,18 +53,11 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
   const int my_tok = t0 + lane;
   const int64_t slot = (lane < kTileTokens && my_tok < num_tokens) ? slot_mapping[my_tok] : -1;
 
-  // Are the tile's tokens (mostly) in consecutive slots?  Every warp holds the same slots -> same answer.
-  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
-  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && slot >= 0 && slot == prev + 1);
-  const bool run_like = __popc(adj) >= kTileTokens / 2;
-
-  if (!run_like) {
-    // ---- decode-like (scattered slots): no staging, no CTA barrier.  warp <-> token, lanes <-> 32-bit words of the
-    //      row, so the stores of one instruction stay inside one (block, head) tile; the rows of all of this warp's
-    //      tokens are loaded before the first store (one memory round trip after the slots). ----
-    constexpr int kTok = kTileTokens / (kTileThreads / 32);   // tokens per warp
-    constexpr int kMaxWords = 4;                              // head_size <= 256
-    uint32_t kw[kTok][kMaxWords], vw[kTok][kMaxWords];
+  // rows of this warp's tokens, warp <-> token, lanes <-> 32-bit words (the scattered path's mapping)
+  constexpr int kTok = kTileTokens / (kTileThreads / 32);   // tokens per warp
+  constexpr int kMaxWords = 4;                              // head_size <= 256
+  uint32_t kw[kTok][kMaxWords], vw[kTok][kMaxWords];
+  auto load_rows = [&]() {
 #pragma unroll
     for (int n = 0; n < kTok; ++n) {
       const int tok = warp + n * (kTileThreads / 32);
@@ -81,6 +73,19 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
         }
       }
     }
+  };
+  if constexpr (kEager) load_rows();   // in flight together with the slot load: one round trip for either path
+
+  // Are the tile's tokens (mostly) in consecutive slots?  Every warp holds the same slots -> same answer.
+  const int64_t prev = __shfl_up_sync(0xffffffffu, slot, 1);
+  const unsigned adj = __ballot_sync(0xffffffffu, lane > 0 && slot >= 0 && slot == prev + 1);
+  const bool run_like = __popc(adj) >= kTileTokens / 2;
+
+  if (!run_like) {
+    // ---- decode-like (scattered slots): no staging, no CTA barrier.  warp <-> token, lanes <-> 32-bit words of the
+    //      row, so the stores of one instruction stay inside one (block, head) tile; the rows of all of this warp's
+    //      tokens are loaded before the first store. ----
+    if constexpr (!kEager) load_rows();
 #pragma unroll
     for (int n = 0; n < kTok; ++n) {
       const int tok = warp + n * (kTileThreads / 32);
@@ -104,6 +109,21 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
     return;
   }
 
+  if constexpr (kEager) {
+    // the rows are already in registers: park them (32-bit words) instead of re-reading them with 128-bit loads
+#pragma unroll
+    for (int n = 0; n < kTok; ++n) {
+      const int tok = warp + n * (kTileThreads / 32);
+#pragma unroll
+      for (int u = 0; u < kMaxWords; ++u) {
+        const int i = lane + 32 * u;
+        if (t0 + tok < num_tokens && i < head_size / 2) {
+          reinterpret_cast<uint32_t*>(ks + tok * pitch)[i] = kw[n][u];
+          vs[tok * vpitch + i] = vw[n][u];
+        }
+      }
+    }
+  } else {
   // ---- prefill-like.  Phase 1: coalesced 128-bit row loads -> smem.  All loads of a batch are issued before the
   //      first store so a thread pays one memory round trip per batch. ----
   const int nchunks = kTileTokens * groups;
@@ -132,6 +152,7 @@ __global__ void __launch_bounds__(kTileThreads) reshape_and_cache_tile_kernel(
         vr[3] = vv[u].w;
       }
     }
+  }
   }
   __syncthreads();
 
@@ -264,11 +285,21 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
       count_launch();
       return VB200_OK;
     }
-    const int tt = mode == 2 ? 16 : mode == 3 ? 32 : (num_tokens <= 2048 ? 16 : 32);   // small batches: smaller tiles
+    const int tt = (mode == 2 || mode == 6 || mode == 8) ? 16
+                   : (mode == 3 || mode == 7 || mode == 9) ? 32 : (num_tokens <= 2048 ? 16 : 32);
     const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
     dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
-    auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16> : reshape_and_cache_tile_kernel<32>;
-    VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(kTileThreads), (size_t)smem, s, static_cast<const __half*>(key),
+    auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 128> : reshape_and_cache_tile_kernel<32, 128>;
+    int threads = 128;
+#ifdef VB200_EXPERIMENTS
+    if (mode == 6 || mode == 7) {   // tried: twice the warps per tile (half the tokens per warp)
+      kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 256> : reshape_and_cache_tile_kernel<32, 256>;
+      threads = 256;
+    }
+    if (mode == 8 || mode == 9)     // tried: row loads issued before the slots are known, registers -> smem
+      kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 128, true> : reshape_and_cache_tile_kernel<32, 128, true>;
+#endif
+    VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(threads), (size_t)smem, s, static_cast<const __half*>(key),
                                    static_cast<const __half*>(value), static_cast<__half*>(key_cache),
                                    static_cast<__half*>(value_cache), slot_mapping, num_tokens, num_heads, head_size,
                                    block_size, key_stride, value_stride));

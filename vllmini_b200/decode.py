@@ -242,8 +242,16 @@ class GPT2Decoder:
     exact-erf GELU as gpt2.py:123), so `load_state_dict` accepts a reference state_dict."""
 
     def __init__(self, shape: GPT2Shape, device: torch.device, dtype=torch.float16, fused_append: bool = True,
-                 fused_layernorm: bool = True):
+                 fused_layernorm: bool = True, prefill_attention: str = "sdpa"):
+        if prefill_attention not in ("sdpa", "paged"):
+            raise ValueError("prefill_attention must be 'sdpa' or 'paged'")
         self.shape, self.device, self.dtype = shape, device, dtype
+        # prefill attention: "sdpa" = a library kernel over the prompt's own q/k/v (what the reference does with
+        # eager matmuls, gpt2.py:46-59, 71-78); "paged" = through the paged path (SURVEY.md 8f rank 4): after
+        # reshape_and_cache has scattered the prompt, paged_attention_v1 is called with one ROW per prompt token
+        # -- every row shares the sequence's block table and row t has seq_len t + 1 -- which is causal attention
+        # over the paged cache, with exactly the arithmetic of the decode steps that follow
+        self.prefill_attention = prefill_attention
         # decode: one fused launch per layer (scatter + attention) instead of the reference's two calls
         self.fused_append = fused_append
         # decode: residual add + LayerNorm (and the embedding sum + ln_1) as one launch each instead of two
@@ -293,24 +301,39 @@ class GPT2Decoder:
         return F.linear(F.gelu(h), self.w[p + "mlp.c_proj.weight"], self.w[p + "mlp.c_proj.bias"])
 
     # -- prefill: one sequence, causal attention over the prompt + reshape_and_cache -----------------------
-    def _prefill_forward(self, input_ids: torch.Tensor, slot_maps, kv: BatchedKVState, last: torch.Tensor):
+    def _prefill_forward(self, input_ids: torch.Tensor, slot_maps, kv: BatchedKVState, last: torch.Tensor,
+                         tables: torch.Tensor = None):
         """input_ids [T], slot_maps[layer] [T] (-1 = padding), `last` int64 [1] (index of the last real token)
-        -> logits of that position [vocab]."""
+        -> logits of that position [vocab].  `tables` [L, MB]: the sequence's block-table rows (paged prefill)."""
         s = self.shape
         T = input_ids.numel()
         H, D = s.n_head, s.head_size
         x = self.w["transformer.wte.weight"][input_ids] + self.w["transformer.wpe.weight"][:T]
+        paged = self.prefill_attention == "paged"
+        if paged:
+            # row t attends over tokens 0..t; padding rows (t > last) attend over nothing and yield zeros
+            pos = torch.arange(T, device=self.device)
+            row_lens = torch.where(pos <= last, pos + 1, torch.zeros_like(pos)).to(torch.int32)
+            max_seq_len = kv.max_blocks_per_seq * kv.block_size
         for i in range(s.n_layer):
             p = f"transformer.h.{i}."
             qkv = F.linear(self._ln(x, p + "ln_1"), self.w[p + "attn.c_attn.weight"], self.w[p + "attn.c_attn.bias"])
             q, k, v = (t.view(T, H, D) for t in qkv.split(s.n_embd, dim=-1))      # strided views, stride 3*E
             ops.reshape_and_cache(k, v, kv.key_cache, kv.value_cache, slot_maps[i], "auto", 1.0)
-            # causal attention over the prompt (gpt2.py:46-59, 71-78): a library kernel, not the paged path.  The
-            # memory-efficient backend is pinned: cuDNN's builds a plan per prompt length (45-95 ms each on B200).
-            with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):
-                o = F.scaled_dot_product_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None],
-                                                   v.transpose(0, 1)[None], is_causal=True, scale=self.scale)[0]
-            o = o.transpose(0, 1).reshape(T, s.n_embd)
+            if paged:
+                # prefill THROUGH the paged path: T rows share one block table; K/V come from the cache just written
+                o = torch.empty((T, H, D), dtype=self.dtype, device=self.device)
+                ops.paged_attention_v1(o, q, kv.key_cache, kv.value_cache, H, self.scale,
+                                       tables[i].expand(T, -1).contiguous(), row_lens, kv.block_size, max_seq_len,
+                                       None, "auto", 1.0, 0, 0, 1, 1, 0)
+            else:
+                # causal attention over the prompt (gpt2.py:46-59, 71-78): a library kernel.  The memory-efficient
+                # backend is pinned: cuDNN's builds a plan per prompt length (45-95 ms each on B200).
+                with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):
+                    o = F.scaled_dot_product_attention(q.transpose(0, 1)[None], k.transpose(0, 1)[None],
+                                                       v.transpose(0, 1)[None], is_causal=True, scale=self.scale)[0]
+                o = o.transpose(0, 1)
+            o = o.reshape(T, s.n_embd)
             x = x + F.linear(o, self.w[p + "attn.c_proj.weight"], self.w[p + "attn.c_proj.bias"])
             x = x + self._mlp(self._ln(x, p + "ln_2"), p)
         x = self._ln(x.index_select(0, last), "transformer.ln_f")
@@ -329,7 +352,7 @@ class GPT2Decoder:
         slot_maps = kv.add_sequence(seq, T)
         if graph_bucket <= 0 or self.device.type != "cuda":
             last = torch.full((1,), T - 1, dtype=torch.int64, device=self.device)
-            return self._prefill_forward(input_ids, slot_maps, kv, last)
+            return self._prefill_forward(input_ids, slot_maps, kv, last, kv.d_tables[:, seq])
         Tb = min((T + graph_bucket - 1) // graph_bucket * graph_bucket, self.shape.n_positions)
         key = (Tb, id(kv))
         st = self._prefill_graphs.get(key)
@@ -340,23 +363,25 @@ class GPT2Decoder:
             st = {"kv": weakref.ref(kv),
                   "ids": torch.zeros(Tb, dtype=torch.int64, device=self.device),
                   "slots": torch.full((L, Tb), -1, dtype=torch.int64, device=self.device),
+                  "tables": torch.full((L, kv.max_blocks_per_seq), -1, dtype=torch.int32, device=self.device),
                   "last": torch.zeros(1, dtype=torch.int64, device=self.device)}
             rows = [st["slots"][l] for l in range(L)]
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):                              # warm-up outside capture (all slots -1)
-                self._prefill_forward(st["ids"], rows, kv, st["last"])
+                self._prefill_forward(st["ids"], rows, kv, st["last"], st["tables"])
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             st["graph"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(st["graph"]):
-                st["logits"] = self._prefill_forward(st["ids"], rows, kv, st["last"])
+                st["logits"] = self._prefill_forward(st["ids"], rows, kv, st["last"], st["tables"])
             self._prefill_graphs[key] = st
         st["ids"].zero_()
         st["ids"][:T].copy_(input_ids)
         st["slots"].fill_(-1)
         st["slots"][:, :T].copy_(torch.stack(slot_maps))
         st["last"].fill_(T - 1)
+        st["tables"].copy_(kv.d_tables[:, seq])
         st["graph"].replay()
         return st["logits"]
 
