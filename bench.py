@@ -509,7 +509,7 @@ def run_continuous(args, dev, world, rank, model, shape):
     for _ in range(5):
         sch.step()
     torch.cuda.synchronize()
-    steps = min(max(args.steps, 20), 100)
+    steps = min(max(args.steps, 60), 100)      # long enough for requests to finish and be replaced inside the window
     if world > 1:
         torch.distributed.barrier()
     tok0, fin0 = sch.tokens_generated, len(sch.finished)

@@ -18,7 +18,8 @@
 namespace vb200 {
 
 // x == 8, head_size % 8 == 0, 16-byte aligned rows.
-// One CTA per (16/32-token tile, head).  The tile's slots are read first and classified (warp ballot):
+// One CTA per (16/32-token tile, head): 16 tokens on 8 warps for 512 < T <= 2048, 32 tokens on 4 warps above.
+// The tile's slots are read first and classified (warp ballot):
 //  * consecutive slots (prefill).  Phase 1: the tile's K and V rows (D halves each) are read with coalesced
 //    128-bit loads and parked in shared memory (row pitch D*2+16 bytes: conflict-free for both access patterns).
 //    Phase 2: lane <-> token.  K: lane stores the 16-byte group g of its token to key_cache[blk][h][g][off][0..7];
@@ -244,7 +245,8 @@ using namespace vb200;
 
 #ifdef VB200_EXPERIMENTS
 // sweep knob of the experiments build (tools/sweep_cache.py): 0 = shipped dispatch, 1 = warp kernel for any size,
-// 2 = 16-token tiles, 3 = 32-token tiles
+// 2 = 16-token tiles on 4 warps, 3 = 32-token tiles, 6 = 16-token tiles on 8 warps (shipped for 512 < T <= 2048),
+// 7 = 32-token tiles on 8 warps, 8 / 9 = eager row loads
 static int g_cache_mode = 0;
 extern "C" int32_t vb200_debug_set_cache_kernel(int32_t mode) {
   const int prev = g_cache_mode;
@@ -285,19 +287,28 @@ extern "C" int vb200_reshape_and_cache_f16(const void* key, const void* value, v
       count_launch();
       return VB200_OK;
     }
+    // 512 < T <= 2048: 16-token tiles on 8 warps (2 tokens per warp) -- scattered batches of that size then run at the
+    // reference kernel's speed (L2 sector-write bound, 0.99x) instead of 0.76x with 4 warps, consecutive slots still
+    // 2x the reference; above that 32-token tiles on 4 warps (profiles/r02g_reshape_and_cache.md)
     const int tt = (mode == 2 || mode == 6 || mode == 8) ? 16
                    : (mode == 3 || mode == 7 || mode == 9) ? 32 : (num_tokens <= 2048 ? 16 : 32);
     const int smem = tt * (head_size * 2 + 16) + tt * (head_size / 2 + 1) * 4;
     dim3 grid(num_heads, (num_tokens + tt - 1) / tt);
-    auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 128> : reshape_and_cache_tile_kernel<32, 128>;
-    int threads = 128;
+    auto kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 256> : reshape_and_cache_tile_kernel<32, 128>;
+    int threads = tt == 16 ? 256 : 128;
 #ifdef VB200_EXPERIMENTS
-    if (mode == 6 || mode == 7) {   // tried: twice the warps per tile (half the tokens per warp)
-      kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 256> : reshape_and_cache_tile_kernel<32, 256>;
+    if (mode == 2) {                // round 2's first dispatch: 16-token tiles on 4 warps
+      kern = reshape_and_cache_tile_kernel<16, 128>;
+      threads = 128;
+    }
+    if (mode == 7) {                // tried: twice the warps per 32-token tile
+      kern = reshape_and_cache_tile_kernel<32, 256>;
       threads = 256;
     }
-    if (mode == 8 || mode == 9)     // tried: row loads issued before the slots are known, registers -> smem
+    if (mode == 8 || mode == 9) {   // tried: row loads issued before the slots are known, registers -> smem
       kern = tt == 16 ? reshape_and_cache_tile_kernel<16, 128, true> : reshape_and_cache_tile_kernel<32, 128, true>;
+      threads = 128;
+    }
 #endif
     VB200_CUDA_CHECK(launch_kernel(kern, grid, dim3(threads), (size_t)smem, s, static_cast<const __half*>(key),
                                    static_cast<const __half*>(value), static_cast<__half*>(key_cache),
