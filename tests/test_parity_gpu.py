@@ -97,6 +97,72 @@ def test_reshape_and_cache_generic_path_unaligned_rows():
     assert np.array_equal(vc_t.cpu().numpy().view(np.uint16), vc_want.view(np.uint16))
 
 
+def _slot_pattern(kind, T, B, NB, rng):
+    """Slot mappings that exercise the tile kernel's classification: whole runs (prefill), runs starting inside a
+    block, short runs glued together (tiles just above / below the half-consecutive threshold), scattered, padding."""
+    if kind == "consecutive":
+        return np.arange(T, dtype=np.int64) + 3 * B
+    if kind == "offset_run":
+        return np.arange(T, dtype=np.int64) + 5 * B + 7
+    if kind == "scattered":
+        return rng.permutation(NB * B)[:T].astype(np.int64)
+    if kind == "short_runs":            # runs of 2..12 consecutive slots at random block offsets, in random order
+        free = rng.permutation(NB)
+        out, b = [], 0
+        while len(out) < T:
+            n = int(rng.integers(2, 13))
+            start = int(free[b]) * B + int(rng.integers(0, B - n + 1)) if n <= B else int(free[b]) * B
+            out.extend(range(start, start + min(n, B)))
+            b += 1
+        return np.asarray(out[:T], dtype=np.int64)
+    if kind == "mixed":                 # first half one run, second half scattered over the remaining blocks, some padding
+        half = T // 2
+        run = np.arange(half, dtype=np.int64)
+        first_free = (half + B - 1) // B
+        rest = rng.permutation((NB - first_free) * B)[: T - half].astype(np.int64) + first_free * B
+        s = np.concatenate([run, rest])
+        s[rng.integers(0, T, size=max(T // 15, 1))] = -1
+        return s
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["consecutive", "offset_run", "scattered", "short_runs", "mixed"])
+@pytest.mark.parametrize("T,B,H,D", [(300, 16, 12, 64),      # warp kernel
+                                     (513, 16, 12, 64), (1500, 8, 3, 80), (2048, 32, 2, 128),   # 16-token tiles, 8 warps
+                                     (2049, 16, 12, 64), (5000, 16, 2, 256)])                   # 32-token tiles
+def test_reshape_and_cache_slot_patterns_bit_exact(kind, T, B, H, D, ref_ext):
+    """Every dispatch regime of reshape_and_cache x every slot pattern its tile classification distinguishes,
+    bit-exact against the C oracle and against the reference's own kernel (cache_kernels.cu:152-207)."""
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(T * 7 + len(kind))
+    NB = max(2 * ((T + B - 1) // B), T // 2) + 16       # short_runs spends one block per 2..12 tokens
+    qkv = rng.standard_normal((T, 3 * H * D)).astype(np.float16)
+    qkv.view(np.uint16)[::89] = 0x7e01
+    slots = _slot_pattern(kind, T, B, NB, rng)
+    live = slots[slots >= 0]
+    assert len(np.unique(live)) == len(live) and live.max() < NB * B
+    k_np, v_np = qkv[:, H * D:2 * H * D].reshape(T, H, D), qkv[:, 2 * H * D:].reshape(T, H, D)
+    kc0 = rng.standard_normal((NB, H, D // 8, B, 8)).astype(np.float16)
+    vc0 = rng.standard_normal((NB, H, D, B)).astype(np.float16)
+    kc_want, vc_want = kc0.copy(), vc0.copy()
+    c_oracle().reshape_and_cache(k_np, v_np, kc_want, vc_want, slots)
+    dev = torch.device("cuda:0")
+    qkv_t = torch.from_numpy(qkv).to(dev)
+    k_t, v_t = qkv_t[:, H * D:2 * H * D].view(T, H, D), qkv_t[:, 2 * H * D:].view(T, H, D)
+    slots_t = torch.from_numpy(slots).to(dev)
+    kc_t, vc_t = torch.from_numpy(kc0).to(dev), torch.from_numpy(vc0).to(dev)
+    ops.reshape_and_cache(k_t, v_t, kc_t, vc_t, slots_t, "auto", 1.0)
+    torch.cuda.synchronize()
+    assert np.array_equal(kc_t.cpu().numpy().view(np.uint16), kc_want.view(np.uint16))
+    assert np.array_equal(vc_t.cpu().numpy().view(np.uint16), vc_want.view(np.uint16))
+    if ref_ext is not None:
+        kc_r, vc_r = torch.from_numpy(kc0).to(dev), torch.from_numpy(vc0).to(dev)
+        ref_ext.cache_ops.reshape_and_cache(k_t, v_t, kc_r, vc_r, slots_t, "auto", 1.0)
+        torch.cuda.synchronize()
+        assert torch.equal(kc_t.view(torch.int16), kc_r.view(torch.int16))
+        assert torch.equal(vc_t.view(torch.int16), vc_r.view(torch.int16))
+
+
 # ------------------------------------------------------------------------------ paged_attention_v1
 @pytest.mark.parametrize("name", [c[0] for c in PARITY_CASES])
 def test_paged_attention_vs_oracle_and_reference_kernel(name, ref_ext):
@@ -117,6 +183,57 @@ def test_paged_attention_vs_oracle_and_reference_kernel(name, ref_ext):
         err_ref = float(np.abs(ref - truth64).max())
         assert err_new <= max(1e-3 + float(np.abs(truth64).max()) * 2.0 ** -10, err_ref), \
             f"{name}: new kernel further from truth ({err_new:.3e}) than the reference kernel ({err_ref:.3e})"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_paged_attention_random_shapes(seed, ref_ext):
+    """Seeded random problems over the reference launcher's whole dispatch table: head size, block size, MHA /
+    grouped-query head counts, batch, ragged lengths (empty sequences included), spare table columns, a max_seq_len
+    hint anywhere between too small and too large (it may only change the split factor), a padded q stride --
+    against the C oracle (fp64 accumulation) and the reference's own kernel."""
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(9000 + seed)
+    D = int(rng.choice([64, 64, 64, 80, 96, 112, 128, 192, 256]))
+    B = int(rng.choice([8, 16, 32]))
+    KVH = int(rng.choice([1, 2, 3, 4, 12]))
+    G = int(rng.choice([1, 1, 2, 4]))
+    H = KVH * G
+    S = int(rng.choice([1, 2, 3, 7, 19, 40]))
+    hi = int(rng.choice([40, 300, 900])) if S > 3 else int(rng.choice([300, 2500, 5000]))
+    lens = rng.integers(0, hi + 1, size=S).astype(np.int32)
+    lens[rng.integers(0, S)] = hi                        # at least one sequence of the full length
+    spare = int(rng.integers(0, 4))
+    nblk = int((int(lens.max()) + B - 1) // B)
+    q, kc, vc, bt, sl = po.make_case(S, KVH, D, B, lens, num_blocks=int(((lens.astype(np.int64) + B - 1) // B).sum()) + 5,
+                                     seed=100 + seed, max_blocks_per_seq=max(nblk, 1) + spare)
+    qpad = int(rng.choice([0, 8, 2 * H * D]))
+    qfull = rng.standard_normal((S, H * D + qpad)).astype(np.float16)
+    q = qfull[:, : H * D].reshape(S, H, D)
+    scale = float(D) ** -0.5
+    # oracle on the MHA-expanded cache (query head h reads kv head h // G)
+    kc_x, vc_x = np.repeat(kc, G, axis=1), np.repeat(vc, G, axis=1)
+    truth = c_oracle().paged_attention_v1(np.ascontiguousarray(q), kc_x, vc_x, scale, bt, sl, mode="exact").astype(np.float64)
+    dev = torch.device("cuda:0")
+    q_t = torch.from_numpy(qfull).to(dev)[:, : H * D].view(S, H, D)
+    kc_t, vc_t, bt_t, sl_t = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (kc, vc, bt, sl))
+    msl = int(rng.choice([1, max(int(lens.max()) // 2, 1), max(int(lens.max()), 1), bt.shape[1] * B, 3 * bt.shape[1] * B]))
+    out = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+    ops.paged_attention_v1(out, q_t, kc_t, vc_t, KVH, scale, bt_t, sl_t, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    what = f"seed {seed}: S={S} H={H}/{KVH} D={D} B={B} lens<= {hi} max_seq_len={msl} qpad={qpad}"
+    err_new = assert_close_to_truth(got, truth, atol=1.5e-3, what=what)
+    for s_ in np.nonzero(sl == 0)[0]:
+        assert not got[s_].any(), what + ": seq_len == 0 row must be zeros"
+    if ref_ext is not None:
+        ref = torch.empty_like(out)
+        ref_ext.paged_attention_v1(ref, q_t, kc_t, vc_t, KVH, scale, bt_t, sl_t, B, int(bt.shape[1]) * B, None, "auto",
+                                   1.0, 0, 0, 1, 1, 0)
+        torch.cuda.synchronize()
+        refn = ref.cpu().numpy().astype(np.float64)
+        diff = np.abs(got.astype(np.float64) - refn)
+        assert (diff <= ATOL_VS_REF + RTOL_VS_REF * np.abs(refn)).all(), what + f": vs reference kernel {diff.max():.3e}"
+        assert err_new <= max(1.5e-3 + float(np.abs(truth).max()) * 2.0 ** -10, float(np.abs(refn - truth).max())), what
 
 
 @pytest.mark.parametrize("max_seq_len", [64, 512, 1280, 2048, 4608])

@@ -323,21 +323,41 @@ __device__ __forceinline__ void cta_merge_and_store(const PaParams& p, const flo
     }
     cluster_sync_all();
     if (split == 0) {
-      const uint32_t base = smem_u32(part);
-      float Mg = -INFINITY;
-      for (int i = 0; i < nsplit_seq; ++i) Mg = fmaxf(Mg, ld_dsmem_f32(dsmem_addr(base + D * 4, i)));
-      float Lg = 0.f;
-      for (int i = 0; i < nsplit_seq; ++i) {
-        const float mi = ld_dsmem_f32(dsmem_addr(base + D * 4, i));
-        Lg += ld_dsmem_f32(dsmem_addr(base + (D + 1) * 4, i)) * ((mi == -INFINITY) ? 0.f : ex2(mi - Mg));
+      // A remote shared-memory read costs ~0.1 us and the cluster holds up to 16 partials, so the reads are spread
+      // and batched instead of looped over: lane i of warp 0 fetches {M_i, L_i} of split i (one round trip for all
+      // splits), the 16 lanes reduce max and sum with a fixed shuffle tree and leave the weights 2^(M_i - M) in this
+      // CTA's shared memory; then thread d fetches o_i[d] of 8 splits at a time, back to back, and accumulates in
+      // split-index order.
+      float* wgt_s = part + D + 2;             // 16 weights + 1 / (L + 1e-6), behind this CTA's own partial
+      if (tid < 32) {
+        const uint32_t base = smem_u32(part);
+        float mi = -INFINITY, li = 0.f;
+        if (tid < nsplit_seq) {
+          mi = ld_dsmem_f32(dsmem_addr(base + D * 4, tid));
+          li = ld_dsmem_f32(dsmem_addr(base + (D + 1) * 4, tid));
+        }
+        float Mg = mi;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) Mg = fmaxf(Mg, __shfl_xor_sync(0xffffffffu, Mg, o));
+        const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
+        float Lg = li * wi;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) Lg += __shfl_xor_sync(0xffffffffu, Lg, o);
+        if (tid < 16) wgt_s[tid] = wi;
+        if (tid == 0) wgt_s[16] = __fdividef(1.f, Lg + 1e-6f);   // reference normaliser (attention_kernels.cu:342)
       }
-      const float inv = __fdividef(1.f, Lg + 1e-6f);   // reference normaliser (attention_kernels.cu:342)
+      __syncthreads();
+      const float inv = wgt_s[16];
       for (int d = tid; d < D; d += W * 32) {
+        const uint32_t mine = smem_u32(part + d);
         float o = 0.f;
-        for (int i = 0; i < nsplit_seq; ++i) {
-          const float mi = ld_dsmem_f32(dsmem_addr(base + D * 4, i));
-          const float wi = (mi == -INFINITY) ? 0.f : ex2(mi - Mg);
-          o += ld_dsmem_f32(dsmem_addr(base + d * 4, i)) * wi;
+#pragma unroll 1
+        for (int i0 = 0; i0 < nsplit_seq; i0 += 8) {
+          float oi[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) oi[u] = (i0 + u < nsplit_seq) ? ld_dsmem_f32(dsmem_addr(mine, i0 + u)) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o += oi[u] * wgt_s[i0 + u];
         }
         p.out[row * D + d] = __float2half_rn(o * inv);
       }
