@@ -31,25 +31,27 @@ def run(name):
     mixed = ctx < 0
     ctx = abs(ctx)
     dev = torch.device("cuda:0")
-    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(2)]
+    kv_bytes = 2 * S * ctx * H * D * 2
+    npools = max(2, min(64, -(-(300 << 20) // kv_bytes)))     # > 2x L2 in total: the traced launch reads from HBM
+    pools = [make(S, H, D, B, ctx, s, dev, mixed=mixed) for s in range(npools)]
     nctas = S * H * 16          # room for a split launch (grid.z <= 16)
-    trace = torch.zeros(nctas * 4, dtype=torch.int64, device=dev)
+    trace = torch.zeros(nctas * 8, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def call(i, tr):
-        q, kc, vc, bt, sl = pools[i % 2]
+        q, kc, vc, bt, sl = pools[i % npools]
         out = torch.empty_like(q)
         lib.vb200_debug_set_trace(tr)
         rc = lib.vb200_paged_attention_v1_f16(out.data_ptr(), q.data_ptr(), kc.data_ptr(), vc.data_ptr(), bt.data_ptr(),
                                               sl.data_ptr(), S, H, H, D, B, bt.shape[1], ctx, q.stride(0), kc.stride(0),
                                               kc.stride(1), D ** -0.5, 0, stream)
         assert rc == 0
-    for i in range(4):
+    for i in range(1, npools + 1):
         call(i, None)
     torch.cuda.synchronize()
     call(0, trace.data_ptr())
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(nctas, 4).astype(np.int64)
+    t = trace.cpu().numpy().reshape(nctas, 8).astype(np.int64)
     t = t[t[:, 3] > 0]          # CTAs that ran (and recorded an end time)
     nctas = len(t)
     t[:, 2] = np.where(t[:, 2] > 0, t[:, 2], t[:, 1])    # a CTA without stages has no first-data time
@@ -81,6 +83,22 @@ def run(name):
     # idle SM-slot time in the tail: for each SM, time between its last CTA end and the span end
     last_end = np.array([t2[smid == s].max() for s in np.unique(smid)])
     rep["sm_idle_at_end_us"] = {"mean": float((span - last_end).mean()), "max": float((span - last_end).max())}
+    # phases of a CTA (us after the launch's first CTA start; p10 / p50 / p90 / max over the CTAs that have the stamp)
+    def pct(x):
+        return [round(float(np.percentile(x, q)), 2) for q in (10, 50, 90, 100)] if len(x) else None
+    def rel(col, ref=None):
+        ok = t[:, col] > 0
+        v = (t[ok, col] - base) / 1e3
+        return pct(v if ref is None else v - ref[ok])
+    rep["phases_us_p10_p50_p90_max"] = {
+        "cta_start": pct(t0), "range_known (seq_len read)": rel(4), "first_stage_landed": pct(t1),
+        "own_stages_done (warp 0)": rel(5), "all_warps_done": rel(6), "after_first_cluster_barrier": rel(7),
+        "cta_end": pct(t2),
+        "start->range_known": rel(4, t0), "range_known->first_stage": pct(t1[t[:, 4] > 0] - (t[t[:, 4] > 0, 4] - base) / 1e3),
+        "first_stage->all_warps_done": pct((t[t[:, 6] > 0, 6] - base) / 1e3 - t1[t[:, 6] > 0]),
+        "all_warps_done->cluster_barrier": rel(7, (t[:, 6] - base) / 1e3) if (t[:, 7] > 0).any() else None,
+        "cluster_barrier->end": pct(t2[t[:, 7] > 0] - (t[t[:, 7] > 0, 7] - base) / 1e3) if (t[:, 7] > 0).any() else None,
+    }
     return rep
 
 
