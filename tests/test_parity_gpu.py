@@ -289,6 +289,62 @@ print('ok')
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_speculative_prefetch_reads_stale_indices():
+    """The first wave of an attention launch prefetches its first ring into L2 AHEAD of griddepcontrol.wait, from
+    seq_lens / block-table entries that the previous kernel on the stream may not have written yet.  Here that
+    previous kernel really is a PDL-aware producer of both tensors (experiments build: lets its dependents launch,
+    holds them for 40 us, then writes the indices): the attention CTAs are resident and speculating on GARBAGE --
+    random int32 block ids (negative, far beyond the pool) and lengths -- the whole time.  The hints must be harmless
+    (no fault, nothing stale left behind) and the result must be the oracle's.  Subprocess: a fault would poison the
+    CUDA context."""
+    import subprocess
+    import sys
+    from vllmini_b200 import build as vb_build, ops
+    ops.reshape_and_cache(*_tiny_reshape_args())          # this process launches something too (autouse check)
+    if not os.path.isfile(vb_build.EXP_LIB_PATH):
+        pytest.skip("no experiments build (python -m vllmini_b200.build --experiments)")
+    code = r"""
+import ctypes, numpy as np, sys, torch
+sys.path.insert(0, 'tests')
+from helpers import assert_close_to_truth
+from oracle import c_oracle, paged_oracle as po
+from vllmini_b200 import _native, ops
+lib = _native.load()
+assert _native.has_experiments()
+fn = lib.vb200_debug_delayed_copy2
+vp, i64, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32
+fn.restype, fn.argtypes = ctypes.c_int32, [vp, vp, i64, vp, vp, i64, u32, vp]
+dev = torch.device('cuda:0')
+rng = np.random.default_rng(77)
+for S, lens_hi, B in ((64, 512, 16), (16, 900, 8), (2, 5000, 32), (200, 300, 16)):
+    lens = rng.integers(1, lens_hi + 1, size=S).astype(np.int32); lens[0] = lens_hi
+    q, kc, vc, bt, sl = po.make_case(S, 12, 64, B, lens, seed=int(S))
+    truth = c_oracle().paged_attention_v1(q, kc, vc, 0.125, bt, sl, mode='exact').astype(np.float64)
+    q_t, kc_t, vc_t, bt_good, sl_good = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (q, kc, vc, bt, sl))
+    for trial in range(3):
+        garbage_bt = torch.from_numpy(rng.integers(-2**31, 2**31, size=bt.shape, dtype=np.int64).astype(np.int32)).to(dev)
+        garbage_sl = torch.from_numpy(rng.integers(-2**31, 2**31, size=sl.shape, dtype=np.int64).astype(np.int32)).to(dev)
+        if trial == 1:
+            garbage_sl.fill_(int(bt.shape[1]) * B)            # plausible lengths, garbage block ids: every hint is wild
+        bt_t, sl_t = garbage_bt.clone(), garbage_sl.clone()
+        out = torch.zeros(S, 12, 64, dtype=torch.float16, device=dev)
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = fn(bt_t.data_ptr(), bt_good.data_ptr(), bt_t.numel(), sl_t.data_ptr(), sl_good.data_ptr(), sl_t.numel(), 40000, st)
+        assert rc == 0
+        ops.paged_attention_v1(out, q_t, kc_t, vc_t, 12, 0.125, bt_t, sl_t, B, int(bt.shape[1]) * B, None, 'auto', 1.0,
+                               0, 0, 1, 1, 0)
+        torch.cuda.synchronize()
+        assert torch.equal(bt_t, bt_good) and torch.equal(sl_t, sl_good)
+        assert_close_to_truth(out.cpu().numpy(), truth, atol=1.5e-3, what=f'S={S} trial {trial}')
+print('ok')
+"""
+    env = dict(os.environ, VLLMINI_B200_LIB=vb_build.EXP_LIB_PATH, VLLMINI_B200_NO_SHIM="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def _tiny_reshape_args():
     dev = torch.device("cuda:0")
     k = torch.zeros(1, 1, 64, dtype=torch.float16, device=dev)

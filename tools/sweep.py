@@ -157,8 +157,11 @@ def main():
     ap.add_argument("--graph", action="store_true", help="time launches replayed from a CUDA graph (no host overhead)")
     ap.add_argument("--merge", default="0", help="experiments build: 0 cluster merge, 1 workspace merge (comma list)")
     ap.add_argument("--max-cluster", default="16", help="experiments build: cap on the cluster size (comma list)")
+    ap.add_argument("--no-spec", action="store_true", help="experiments build: speculative first-ring prefetch off")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     a = ap.parse_args()
+    if a.no_spec:
+        _native.set_spec_prefetch(False)
     global POOL_MULT
     POOL_MULT = a.pool_mult
     res = []

@@ -120,3 +120,13 @@ def set_merge(merge_mode: int = 0, max_cluster: int = 16) -> None:
     fn = lib.vb200_debug_set_merge
     fn.restype, fn.argtypes = None, [_i32, _i32]
     fn(int(merge_mode), int(max_cluster))
+
+
+def set_spec_prefetch(on: bool = True) -> None:
+    """Experiments build only: A/B switch for the speculative first-ring L2 prefetch ahead of griddepcontrol.wait."""
+    lib = load()
+    if not has_experiments():
+        raise RuntimeError("vllmini_b200: this build has no sweep knobs (see set_tuning)")
+    fn = lib.vb200_debug_set_spec_prefetch
+    fn.restype, fn.argtypes = None, [_i32]
+    fn(1 if on else 0)

@@ -148,3 +148,34 @@ extern "C" int vb200_reshape_and_cache_flash_f16(const void* key, const void* va
   VB200_CUDA_CHECK(cudaGetLastError());
   return VB200_OK;
 }
+
+#ifdef VB200_EXPERIMENTS
+// Test helper of the experiments build (tests/test_parity_gpu.py::test_speculative_prefetch_reads_stale_indices): a
+// kernel that behaves like a PDL-aware producer of the index tensors -- it lets its dependents launch at once, keeps
+// them waiting for `delay_ns`, and only then writes the block table and seq_lens.  The attention launch queued behind
+// it is resident (and speculating on whatever the two buffers held before) during the whole delay.
+namespace vb200 {
+__global__ void __launch_bounds__(256) debug_delayed_copy2_kernel(int32_t* dst1, const int32_t* src1, int64_t n1,
+                                                                  int32_t* dst2, const int32_t* src2, int64_t n2,
+                                                                  uint32_t delay_ns) {
+  griddep_launch_dependents();
+  griddep_wait();
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < delay_ns);
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = i0; i < n1; i += step) dst1[i] = src1[i];
+  for (int64_t i = i0; i < n2; i += step) dst2[i] = src2[i];
+}
+}  // namespace vb200
+
+extern "C" int vb200_debug_delayed_copy2(int32_t* dst1, const int32_t* src1, int64_t n1, int32_t* dst2,
+                                         const int32_t* src2, int64_t n2, uint32_t delay_ns, void* stream) {
+  VB200_CUDA_CHECK(vb200::launch_kernel(vb200::debug_delayed_copy2_kernel, dim3(8), dim3(256), 0,
+                                        static_cast<cudaStream_t>(stream), dst1, src1, n1, dst2, src2, n2, delay_ns));
+  return VB200_OK;
+}
+#endif

@@ -215,6 +215,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
+// L2-only load (never allocates in L1): for SPECULATIVE reads ahead of griddepcontrol.wait -- a later ordinary load of
+// the same address must not find a stale line in this SM's L1
+__device__ __forceinline__ int32_t ld_cg_s32(const int32_t* p) {
+  int32_t r;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+// hint: bring the 128-byte line holding p into L2; no destination, no fault on an unmapped address
+// (tools/prefetch_wild_repro.cu)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory"); }
 __device__ __forceinline__ float ld_cg_f32(const float* p) {
   float r;
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");

@@ -51,6 +51,8 @@ struct PaParams {
   float scale_log2e;
   int num_splits;
   int split_tokens;  // multiple of 32; ignored when num_splits == 1
+  int spec_ctas;     // CTAs with a linear block index below this are (likely) resident when the launch starts: they
+                     // prefetch their first stages into L2 ahead of griddepcontrol.wait (0 = nobody does)
   int cluster_merge; // != 0: the num_splits CTAs of a (seq, head) form one thread-block cluster (1, 1, num_splits) and
                      // merge their partials through distributed shared memory -- no workspace, no counters
   // fused append (vb200_paged_attention_v1_append_f16): this step's K/V rows [num_seqs, num_kv_heads, D] are
@@ -395,8 +397,7 @@ struct UnitRange {
   bool empty_split;  // split > 0 and no token in it: nothing to do, nobody waits for it
 };
 template <int B>
-__device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int split) {
-  int len = p.seq_lens[seq];
+__device__ __forceinline__ UnitRange unit_range_of_len(const PaParams& p, int len, int split) {
   len = len < p.max_blocks_per_seq * B ? len : p.max_blocks_per_seq * B;  // never read past the table row
   const bool v2 = p.v2_exp_sums != nullptr;
   const bool parts = p.num_splits > 1 || v2;
@@ -418,6 +419,11 @@ __device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int 
     r.nsplit_seq = n < p.num_splits ? n : p.num_splits;
   }
   return r;
+}
+
+template <int B>
+__device__ __forceinline__ UnitRange unit_range(const PaParams& p, int seq, int split) {
+  return unit_range_of_len<B>(p, p.seq_lens[seq], split);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,6 +452,39 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
 #pragma unroll
     for (int i = 0; i < W * NST; ++i) mbar_init(smem_u32(smem + PaCfg<D, B, W, NST>::BAR_OFF) + i * 8, 1);
     fence_mbar_init();
+  }
+  // ---- speculative L2 prefetch of this warp's first ring, AHEAD of griddepcontrol.wait.  With programmatic
+  //      dependent launch the CTAs of the first wave are resident while the previous kernel on the stream still runs
+  //      (its tail leaves HBM underused); seq_lens and the block table may be that kernel's output, so whatever is
+  //      read here can be stale or garbage -- it is used for HINTS only (prefetch.global.L2: no destination, dropped on
+  //      an unmapped address, tools/prefetch_wild_repro.cu), read with L2-only loads (no stale line is left in L1),
+  //      and everything is read again after the wait.  A prefetched K/V line that the predecessor then writes (the new
+  //      token's slot) is updated in L2, the point of coherence, like any other.  CTAs of later waves start when the
+  //      launch is under way and skip this (their hints would only duplicate the copies that follow). ----
+  if ((int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) < p.spec_ctas) {
+    int len_s = ld_cg_s32(p.seq_lens + seq);
+    len_s = len_s < 0 ? 0 : len_s;
+    const UnitRange rs = unit_range_of_len<B>(p, len_s, split);
+    const int kv_head_s = head / (p.num_heads / p.num_kv_heads);
+    const char* kb = reinterpret_cast<const char*>(p.kc + (int64_t)kv_head_s * p.kv_head_stride);
+    const char* vb = reinterpret_cast<const char*>(p.vc + (int64_t)kv_head_s * p.kv_head_stride);
+    const int32_t* table_s = p.block_tables + (int64_t)seq * p.max_blocks_per_seq + rs.tok_begin / B;
+    constexpr int LINES = C::TILE / 128;   // 128-byte lines per K (or V) tile
+    // (one ring deep: two rings gain less, eight lose on large batches -- profiles/r02j_spec_prefetch.md)
+#pragma unroll
+    for (int k = 0; k < NST; ++k) {
+      const int st = warp + k * W;
+      if (st >= rs.nstages) break;   // (warp-uniform)
+#pragma unroll
+      for (int b = 0; b < C::BPS; ++b) {
+        const int blk = st * C::BPS + b;
+        if (blk < rs.nblk) {
+          const int64_t off = (int64_t)ld_cg_s32(table_s + blk) * p.kv_block_stride * 2;   // bytes
+          for (int l = lane; l < 2 * LINES; l += 32)
+            prefetch_l2(l < LINES ? kb + off + l * 128 : vb + off + (l - LINES) * 128);
+        }
+      }
+    }
   }
   griddep_wait();
 
@@ -949,6 +988,7 @@ struct Tuning {
   int force_splits = 0;
   int variant = 0;
   int max_cluster = 16;  // cap on the cluster size / split factor
+  int spec_prefetch = 1; // speculative first-ring L2 prefetch ahead of griddepcontrol.wait (A/B knob)
 };
 static Tuning g_tuning;
 // 0: default; 1: 4x3; 2: 8x1; 3: 2x2; 4: default kernel with the grouped-query path off
@@ -957,10 +997,12 @@ constexpr int kNumVariants = 5;
 static int tuning_variant() { return g_tuning.variant; }
 static int tuning_force_splits() { return g_tuning.force_splits; }
 static int tuning_max_cluster() { return g_tuning.max_cluster; }
+static int tuning_spec_prefetch() { return g_tuning.spec_prefetch; }
 #else
 static constexpr int tuning_variant() { return 0; }
 static constexpr int tuning_force_splits() { return 0; }
 static constexpr int tuning_max_cluster() { return 16; }
+static constexpr int tuning_spec_prefetch() { return 1; }
 #endif
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): a lock-free
@@ -1004,8 +1046,10 @@ static int launch_classic_impl(const PaParams& p, int num_seqs, cudaStream_t str
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // clusters of up to 16
   }));
+  PaParams pl = p;
+  if (p.spec_ctas) pl.spec_ctas = device_sm_count() * ((227 * 1024) / (C::SMEM + 1024));   // the launch's first wave
   VB200_CUDA_CHECK(launch_kernel_cluster(kern, grid, dim3(W * 32), (size_t)C::SMEM, stream,
-                                         p.cluster_merge ? (unsigned)p.num_splits : 1u, p));
+                                         pl.cluster_merge ? (unsigned)pl.num_splits : 1u, pl));
   count_launch();
   return VB200_OK;
 }
@@ -1278,6 +1322,11 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   p.kv_head_stride = kv_head_stride;
   p.scale_log2e = (float)((double)scale * 1.4426950408889634074);
   p.cluster_merge = 0;
+  // speculative first-ring prefetch (pa_v1_kernel): pays when CTAs are resident before the previous kernel has
+  // finished (PDL) and the K/V they will read is not already in L2; a launch over a few MB gains nothing and pays
+  // ~0.08 us for the two extra index loads (profiles/r02j_spec_prefetch.md)
+  p.spec_ctas = (pdl_enabled() && tuning_spec_prefetch() &&
+                 (int64_t)num_seqs * max_seq_len * num_kv_heads * head_size * 4 >= (int64_t)(4 << 20)) ? 1 : 0;
   int ns = 1, st = 0;
   if (v2) {
     // the reference's fixed 512-token partitions; the partition count is the scratch tensors' stride
@@ -1437,6 +1486,7 @@ extern "C" int32_t vb200_debug_set_tuning(int32_t force_num_splits, int32_t vari
 }
 // cap on the cluster size = split factor (2..16); merge_mode is accepted for old sweep scripts and ignored (round 1's
 // workspace merge was measured against the cluster merge in profiles/r02c_split_merge.md and removed)
+extern "C" void vb200_debug_set_spec_prefetch(int32_t on) { g_tuning.spec_prefetch = on ? 1 : 0; }
 extern "C" void vb200_debug_set_merge(int32_t merge_mode, int32_t max_cluster) {
   (void)merge_mode;
   g_tuning.max_cluster = max_cluster < 1 ? 16 : max_cluster;
