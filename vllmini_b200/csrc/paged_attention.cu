@@ -51,8 +51,8 @@ struct PaParams {
   float scale_log2e;
   int num_splits;
   int split_tokens;  // multiple of 32; ignored when num_splits == 1
-  int spec_ctas;     // CTAs with a linear block index below this are (likely) resident when the launch starts: they
-                     // prefetch their first stages into L2 ahead of griddepcontrol.wait (0 = nobody does)
+  int spec_ctas;     // CTAs with a linear block index below this (= the launch's first wave: SMs x CTAs per SM) prefetch
+                     // their first ring into L2 ahead of griddepcontrol.wait; 0 = nobody does
   int cluster_merge; // != 0: the num_splits CTAs of a (seq, head) form one thread-block cluster (1, 1, num_splits) and
                      // merge their partials through distributed shared memory -- no workspace, no counters
   // fused append (vb200_paged_attention_v1_append_f16): this step's K/V rows [num_seqs, num_kv_heads, D] are
