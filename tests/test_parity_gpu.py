@@ -774,6 +774,56 @@ def test_copy_blocks_and_swap_blocks_bit_exact(ref_ext):
 
 
 # ------------------------------------------------------------------------------ fused append + attend
+@pytest.mark.parametrize("seed", range(10))
+def test_fused_append_random_shapes(seed):
+    """Seeded random decode steps through the fused launch: head size, block size, MHA / grouped-query, batch (from a
+    split-KV handful to several hundred rows, the latter large enough for the speculative first-ring prefetch),
+    histories from brand-new sequences to a few thousand tokens, both position conventions -- caches and output bit
+    for bit equal to reshape_and_cache + paged_attention_v1, output against the C oracle on the updated cache."""
+    from vllmini_b200 import ops
+    rng = np.random.default_rng(4000 + seed)
+    D = int(rng.choice([64, 64, 80, 96, 112, 128, 192, 256]))
+    B = int(rng.choice([8, 16, 32]))
+    KVH = int(rng.choice([1, 2, 4, 12]))
+    G = int(rng.choice([1, 1, 2, 4]))
+    H = KVH * G
+    S = int(rng.choice([1, 2, 5, 33, 150, 300]))
+    hi = int(rng.choice([60, 400])) if S > 5 else int(rng.choice([400, 3000]))
+    hist = rng.integers(0, hi + 1, size=S)
+    hist[rng.integers(0, S)] = 0                              # a brand-new sequence
+    hist[rng.integers(0, S)] = hi
+    self_attend = bool(seed % 2)
+    lens_after = hist + 1
+    q, kc, vc, bt, _ = po.make_case(S, KVH, D, B, lens_after, seed=500 + seed,
+                                    max_blocks_per_seq=int(lens_after.max() // B + 2))
+    q = rng.standard_normal((S, H, D)).astype(np.float16)
+    dev = torch.device("cuda:0")
+    new_qkv = torch.from_numpy(rng.standard_normal((S, (H + 2 * KVH) * D)).astype(np.float16)).to(dev)
+    k_new = new_qkv[:, H * D:(H + KVH) * D].view(S, KVH, D)
+    v_new = new_qkv[:, (H + KVH) * D:].view(S, KVH, D)
+    slots = torch.from_numpy(bt[np.arange(S), hist // B].astype(np.int64) * B + hist % B).to(dev)
+    seq_lens_np = (lens_after if self_attend else hist).astype(np.int32)
+    seq_lens = torch.from_numpy(seq_lens_np).to(dev)
+    bt_t, q_t = torch.from_numpy(bt).to(dev), torch.from_numpy(q).to(dev)
+    msl = int(bt.shape[1]) * B
+    scale = float(D) ** -0.5
+    kc_a, vc_a = torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev)
+    out_a = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+    ops.reshape_and_cache(k_new, v_new, kc_a, vc_a, slots, "auto", 1.0)
+    ops.paged_attention_v1(out_a, q_t, kc_a, vc_a, KVH, scale, bt_t, seq_lens, B, msl, None, "auto", 1.0, 0, 0, 1, 1, 0)
+    kc_b, vc_b = torch.from_numpy(kc).to(dev), torch.from_numpy(vc).to(dev)
+    out_b = torch.empty(S, H, D, dtype=torch.float16, device=dev)
+    ops.paged_attention_v1_append(out_b, q_t, k_new, v_new, kc_b, vc_b, slots, KVH, scale, bt_t, seq_lens, B, msl)
+    torch.cuda.synchronize()
+    what = f"seed {seed}: S={S} H={H}/{KVH} D={D} B={B} hist<= {hi} self_attend={self_attend}"
+    assert torch.equal(kc_a, kc_b) and torch.equal(vc_a, vc_b), what + ": fused scatter differs from reshape_and_cache"
+    assert torch.equal(out_a, out_b), what + ": fused attention differs from the two-launch result"
+    kc_x = np.repeat(kc_a.cpu().numpy(), G, axis=1)
+    vc_x = np.repeat(vc_a.cpu().numpy(), G, axis=1)
+    truth = c_oracle().paged_attention_v1(q, kc_x, vc_x, scale, bt, seq_lens_np, mode="exact").astype(np.float64)
+    assert_close_to_truth(out_b.cpu().numpy(), truth, atol=1.5e-3, what=what)
+
+
 @pytest.mark.parametrize("self_attend", [True, False])
 @pytest.mark.parametrize("shape", ["batch", "long_small_batch", "gqa", "head80_blk8", "head256_blk32"])
 def test_fused_append_equals_reshape_then_attention(self_attend, shape):
