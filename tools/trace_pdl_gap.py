@@ -72,6 +72,14 @@ def run(name, pdl):
                          "first_wait_released": round(float(us(4).min()), 2),
                          "first_data_p50": round(float(np.median(us(2))), 2),
                          "last_cta_end": round(float(us(3).max()), 2)}
+    # launch B in detail: us after its griddepcontrol.wait was first released, p10 / p50 / p90 over its CTAs
+    tb = ts[1]
+    rel = tb[tb[:, 4] > 0, 4].min()
+    def pct(c):
+        v = (tb[tb[:, c] > 0, c] - rel) / 1e3
+        return [round(float(np.percentile(v, q)), 2) for q in (10, 50, 90)] if len(v) else None
+    rep["B after release"] = {"seq_len known": pct(4), "first stage landed": pct(2), "own stages done (warp 0)": pct(5),
+                              "all warps done": pct(6), "cta end": pct(3)}
     for a, b in ("AB", "BC"):
         rep[f"{a}.last_end -> {b}.wait_released"] = round(rep[b]["first_wait_released"] - rep[a]["last_cta_end"], 2)
         rep[f"{a}.last_end -> {b}.last_end (period)"] = round(rep[b]["last_cta_end"] - rep[a]["last_cta_end"], 2)

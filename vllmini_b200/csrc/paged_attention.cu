@@ -543,9 +543,9 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
     return (lane < C::BPS && blk < nblk) ? __ldg(table + blk) : 0;
   };
 
-  // prologue: fill the ring.  (Fetching these table entries speculatively, together with seq_len, was measured
-  // twice -- profiles/r01i_cta_timeline.md, profiles/r02d_spec_table_prefetch.md -- and gains nothing: both loads
-  // are L2 hits, the wait for the first stage is HBM queueing.)
+  // prologue: fill the ring.  (Fetching these table entries together with seq_len -- one dependent round trip less --
+  // was measured three times, the last time with the first ring already prefetched into L2: profiles/
+  // r01i_cta_timeline.md, r02d_spec_table_prefetch.md, r02j_spec_prefetch.md -- and gains nothing.)
   {
     int ph[NST];
 #pragma unroll
