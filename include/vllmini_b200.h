@@ -201,7 +201,13 @@ uint64_t vb200_launch_count(void);
 /* Programmatic dependent launch (default on): kernels are launched so that their CTAs may become resident
  * while the previous kernel on the stream drains, and block (griddepcontrol.wait) until it has completed
  * before reading or writing global memory -- stream-order semantics are unchanged.  Returns the previous
- * setting.  Turn off if a tool or driver in the stack mishandles programmatic launch attributes. */
+ * setting.  Turn off if a tool or driver in the stack mishandles programmatic launch attributes.
+ *
+ * With it on, vb200_paged_attention_v1* / v2 launches over more than 4 MB of K/V also issue L2 PREFETCH HINTS ahead of
+ * that wait: the first wave of CTAs reads seq_lens / block_tables entries as they are at that moment (L2-only loads) and
+ * hints the K/V tiles they name.  Hints have no architectural effect -- stale or uninitialised indices make them
+ * useless, not wrong; every value is read again after the wait.  Both index tensors only have to be valid allocations
+ * when the call is enqueued.  Off together with programmatic launch. */
 int32_t vb200_set_pdl(int32_t enable);
 
 #ifdef __cplusplus

@@ -23,6 +23,7 @@
 // bulk copy moves a whole tile.  A lane reads 16-byte chunks c = lane + 32*j of a tile:
 //   K chunk c -> token c % B, dims 8*(c / B) .. +7        (lane owns ONE token, D*B/256 dim groups)
 //   V chunk c -> row   c / (B/8), tokens 8*(c % (B/8)) .. +7  (lane owns D*B/256 rows, 8 tokens)
+#include <algorithm>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -1325,8 +1326,9 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
   // speculative first-ring prefetch (pa_v1_kernel): pays when CTAs are resident before the previous kernel has
   // finished (PDL) and the K/V they will read is not already in L2; a launch over a few MB gains nothing and pays
   // ~0.08 us for the two extra index loads (profiles/r02j_spec_prefetch.md)
+  const int64_t ctx_bound = std::min<int64_t>(max_seq_len, (int64_t)max_num_blocks_per_seq * block_size);
   p.spec_ctas = (pdl_enabled() && tuning_spec_prefetch() &&
-                 (int64_t)num_seqs * max_seq_len * num_kv_heads * head_size * 4 >= (int64_t)(4 << 20)) ? 1 : 0;
+                 (int64_t)num_seqs * ctx_bound * num_kv_heads * head_size * 4 >= (int64_t)(4 << 20)) ? 1 : 0;
   int ns = 1, st = 0;
   if (v2) {
     // the reference's fixed 512-token partitions; the partition count is the scratch tensors' stride
