@@ -380,6 +380,68 @@ def test_two_streams_splitting_concurrently():
             assert_close_to_truth(o[i].cpu().numpy(), truth, what=f"stream-concurrent split-KV, call {i}")
 
 
+def test_host_threads_calling_concurrently():
+    """Four host threads, each on its own stream, call the C ABI through the ctypes binding (which releases the GIL)
+    at the same time: first-use initialisation (function attributes, the cluster-size query), the launch counter and
+    the per-thread error text must hold up, and every result must be the single-threaded one.  Shapes differ per
+    thread so that different instantiations are initialised concurrently; one thread keeps provoking an error."""
+    import threading
+    from vllmini_b200 import _native, ops
+    dev = torch.device("cuda:0")
+    specs = [("ragged_small", None), ("head128_bs16", None), ("ctx_mixed_long", 4608), ("head80_bs8", None)]
+    work = []
+    for name, msl in specs:
+        c = build_case(name)
+        t = to_cuda(c)
+        want = run_cuda_attention(c, t, max_seq_len=msl)          # single-threaded result, default stream
+        work.append((c, t, msl, want))
+    lib = _native.load()
+    errors, results = [], [None] * len(work)
+    barrier = threading.Barrier(len(work))
+
+    def body(i):
+        try:
+            c, t, msl, _ = work[i]
+            st = torch.cuda.Stream(dev)
+            outs = []
+            barrier.wait()
+            with torch.cuda.stream(st):
+                for it in range(150):
+                    out = torch.empty((c["S"], c["H"], c["D"]), dtype=torch.float16, device=dev)
+                    rc = lib.vb200_paged_attention_v1_f16(
+                        out.data_ptr(), t["q"].data_ptr(), t["kc"].data_ptr(), t["vc"].data_ptr(), t["bt"].data_ptr(),
+                        t["sl"].data_ptr(), c["S"], c["H"], c["kc"].shape[1], c["D"], c["B"], int(t["bt"].shape[1]),
+                        msl or int(t["bt"].shape[1]) * c["B"], t["q"].stride(0), t["kc"].stride(0), t["kc"].stride(1),
+                        float(c["scale"]), 0, st.cuda_stream)
+                    assert rc == 0, _native.last_error()
+                    outs.append(out)
+                    if i == 0 and it % 10 == 0:                    # an error on this thread: its text stays this thread's
+                        rc = lib.vb200_paged_attention_v1_f16(
+                            out.data_ptr(), t["q"].data_ptr(), t["kc"].data_ptr(), t["vc"].data_ptr(), t["bt"].data_ptr(),
+                            t["sl"].data_ptr(), c["S"], c["H"], c["kc"].shape[1], 72, c["B"], int(t["bt"].shape[1]),
+                            64, t["q"].stride(0), t["kc"].stride(0), t["kc"].stride(1), 0.1, 0, st.cuda_stream)
+                        assert rc != 0 and "head size" in _native.last_error()
+                    elif it % 10 == 0:
+                        assert "head size" not in _native.last_error()
+            st.synchronize()
+            results[i] = [o.cpu().numpy() for o in (outs[0], outs[len(outs) // 2], outs[-1])]
+        except Exception as e:                                       # surfaced in the main thread
+            errors.append((i, repr(e)))
+
+    n0 = _native.launch_count()
+    threads = [threading.Thread(target=body, args=(i,)) for i in range(len(work))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    assert _native.launch_count() - n0 == 150 * len(work)
+    for (c, t, msl, want), got in zip(work, results):
+        for g in got:
+            assert np.array_equal(g.view(np.uint16), want.view(np.uint16)), "result differs from the single-threaded call"
+
+
 def test_small_batch_long_context_uses_split_kv():
     """S*H far below the SM count: the launcher splits the context (flash-decoding style) -- the splits of a
     (sequence, head) form a thread-block cluster and merge through distributed shared memory -- and must reproduce
