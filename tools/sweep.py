@@ -59,6 +59,12 @@ CONFIGS = {
     "S128_256": (128, 12, 64, 16, 256),
     "S128_1k": (128, 12, 64, 16, 1024),
     "S8_2k": (8, 12, 64, 16, 2048),
+    # small batches at head sizes that hold 2 / 1 CTAs per SM (split factor capped by the resident slots)
+    "D128_s16_1k": (16, 8, 128, 16, 1024),
+    "D96_s40_1k": (40, 3, 96, 32, 1024),
+    "D256_s10_2k": (10, 10, 256, 16, 2048),
+    "D112_s2_3k": (2, 12, 112, 8, 3008, 24),
+    "D192_s6_2k": (6, 8, 192, 16, 2048),
 }
 
 

@@ -13,7 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-// mode 0: one barrier, one phase.  mode 1: the product's pattern -- every warp owns a ring of two 1 KB slots with one
+// mode 0: one barrier, one phase.  mode 2 = mode 1 on a grid of 4800 clusters (several waves).  mode 1: the product's pattern -- every warp owns a ring of two 1 KB slots with one
 // mbarrier each and streams `rounds` stages through it (lane 0: arrive.expect_tx + bulk copy; all lanes: try_wait on
 // the slot's parity; refill after use), the ranks of a cluster running different numbers of rounds.
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) repro_kernel(const uint32_t* __restrict__
     if (threadIdx.x == 0) issue_copy(buf0, src + 256 * blockIdx.z, bar0);
     mbar_wait_parity(bar0, 0);
     s = buf[threadIdx.x] + buf[threadIdx.x + 128];
-  } else {
+  } else {   // modes 1 and 2
     const int rounds = 3 + (int)(blockIdx.z % 5);          // stages of this warp; ranks differ
     const uint32_t* mine = src + 256 * blockIdx.z;          // every stage re-reads the rank's 1 KB
     const uint32_t wbar = bar0 + warp * 16, wbuf = buf0 + warp * 2048;
@@ -94,7 +94,8 @@ int main(int argc, char** argv) {
     if (n < 1 || n > max_n) continue;
     cudaMemset(out, 0, 8);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(12, 2, n);   // several clusters, like the product's (heads, seqs, splits)
+    // several clusters, like the product's (heads, seqs, splits); mode 2: more clusters than the GPU holds at once
+    cfg.gridDim = dim3(12, mode == 2 ? 400 : 2, n);
     cfg.blockDim = dim3(128);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -108,9 +109,9 @@ int main(int argc, char** argv) {
     uint32_t r[2] = {0, 0};
     cudaMemcpy(r, out, 8, cudaMemcpyDeviceToHost);
     uint32_t want = 0;
-    for (int i = 0; i < n * 256; ++i) want += 24 * h[i];
+    for (int i = 0; i < n * 256; ++i) want += (mode == 2 ? 4800u : 24u) * h[i];
     printf("mode %d cluster (1,1,%d): launch=%s sync=%s checksum %s (%u), sum of address rank bits %u (expect %d)\n", mode, n,
-           cudaGetErrorString(e), cudaGetErrorString(e2), r[0] == want ? "ok" : "WRONG", r[0], r[1], 24 * n * (n - 1) / 2);
+           cudaGetErrorString(e), cudaGetErrorString(e2), r[0] == want ? "ok" : "WRONG", r[0], r[1], (mode == 2 ? 4800 : 24) * n * (n - 1) / 2);
   }
   return 0;
 }

@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -231,20 +232,28 @@ __device__ __forceinline__ void process_stage(uint32_t sbase, uint32_t pbuf, int
   __syncwarp();
 }
 
-// Issue the bulk copies of one stage: lane i < 2*BPS issues copy i (K tiles 0..BPS-1, then V tiles).
+// Issue the bulk copies of one stage (K and V tile of each block that exists).
 // `phys`: lane b < BPS holds the physical block id of block b of the stage; nb = blocks that exist.
 template <class C>
 __device__ __forceinline__ void issue_stage_copies(uint32_t dst_stage, uint32_t bar, int lane, int phys, int nb,
                                                    const __half* kbase, const __half* vbase,
                                                    int64_t kv_block_stride) {
-  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(2 * nb * C::TILE));
-  __syncwarp();
-  const int b = lane % C::BPS;
-  const int is_v = lane / C::BPS;
-  const int phys_b = __shfl_sync(0xffffffffu, phys, b);
-  if (lane < 2 * C::BPS && b < nb) {
-    const __half* src = (is_v ? vbase : kbase) + (int64_t)phys_b * kv_block_stride;
-    bulk_g2s(dst_stage + (is_v * C::BPS + b) * C::TILE, src, C::TILE, bar);
+  // All operands of the copies are warp-uniform (constant-lane shuffles, a warp index broadcast from lane 0), and one
+  // elected lane issues them in straight-line code: the compiler can keep addresses in uniform registers instead of
+  // looping over the lanes that each hold one copy.
+  int pb[C::BPS];
+#pragma unroll
+  for (int b = 0; b < C::BPS; ++b) pb[b] = __shfl_sync(0xffffffffu, phys, b);
+  if (elect_one()) {
+    mbar_arrive_expect_tx(bar, (uint32_t)(2 * nb * C::TILE));
+#pragma unroll
+    for (int b = 0; b < C::BPS; ++b) {
+      if (b < nb) {
+        const int64_t off = (int64_t)pb[b] * kv_block_stride;
+        bulk_g2s(dst_stage + b * C::TILE, kbase + off, C::TILE, bar);
+        bulk_g2s(dst_stage + (C::BPS + b) * C::TILE, vbase + off, C::TILE, bar);
+      }
+    }
   }
 }
 
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
   const int seq = blockIdx.y;
   const int split = blockIdx.z;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // broadcast: warp-uniform for the compiler
 
   // PDL: this CTA may have become resident while the previous kernel on the stream was still draining.  Let
   // our own successor do the same, set up the barriers, then wait for the predecessor before the first global
@@ -486,6 +495,7 @@ __global__ void __launch_bounds__(W * 32) pa_v1_kernel(const PaParams p) {
         }
       }
     }
+    __syncwarp();   // 2 * LINES need not be a multiple of 32: converge again before the CTA barrier below
   }
   griddep_wait();
 
@@ -991,7 +1001,18 @@ struct Tuning {
   int max_cluster = 16;  // cap on the cluster size / split factor
   int spec_prefetch = 1; // speculative first-ring L2 prefetch ahead of griddepcontrol.wait (A/B knob)
 };
-static Tuning g_tuning;
+static Tuning make_tuning() {
+  Tuning t;
+  // VB200_MAX_CLUSTER=8: lets a whole test run stay within the cluster sizes compute-sanitizer's synccheck can follow
+  // (profiles/r02f_sanitizer.md); experiments build only
+  if (const char* e = getenv("VB200_MAX_CLUSTER")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) t.max_cluster = v;
+  }
+  if (const char* e = getenv("VB200_SPEC_PREFETCH")) t.spec_prefetch = atoi(e) ? 1 : 0;
+  return t;
+}
+static Tuning g_tuning = make_tuning();
 // 0: default; 1: 4x3; 2: 8x1; 3: 2x2; 4: default kernel with the grouped-query path off
 static constexpr Shape kVariants[] = {{0, 2}, {4, 3}, {8, 1}, {2, 2}, {0, 2}};
 constexpr int kNumVariants = 5;
@@ -1094,6 +1115,54 @@ static int cluster_cap() {
   cached[dev].store(cap, std::memory_order_release);
   return cap;
 }
+// How many (1, 1, n) clusters of the default kernel of head size D the device holds at once (co-scheduling inside a
+// GPC makes this less than slots / n: 48 clusters of 3 do not fit 148 one-CTA SMs).  Queried once per (device, n).
+template <int D>
+static int max_active_clusters(int n) {
+  constexpr int W = (D == 64 || D == 96 || D == 192) ? 4 : 3;
+  using C = PaCfg<D, 16, W, 2>;
+  auto kern = pa_v1_kernel<D, 16, W, 2, false>;
+  static std::atomic<int> cached[64][17];
+  int dev = 0;
+  if (n < 2 || n > 16 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return 1 << 30;   // unknown: do not constrain
+  }
+  int v = cached[dev][n].load(std::memory_order_acquire);
+  if (v) return v - 1;
+  int num = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, (unsigned)n);
+  cfg.blockDim = dim3(W * 32);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)n;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&num, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    num = (1 << 30) - 1;
+  }
+  cached[dev][n].store(num + 1, std::memory_order_release);
+  return num;
+}
+static int max_active_clusters_for(int head_size, int n) {
+  switch (head_size) {
+    case 64: return max_active_clusters<64>(n);
+    case 80: return max_active_clusters<80>(n);
+    case 96: return max_active_clusters<96>(n);
+    case 112: return max_active_clusters<112>(n);
+    case 128: return max_active_clusters<128>(n);
+    case 192: return max_active_clusters<192>(n);
+    default: return max_active_clusters<256>(n);
+  }
+}
+
 static int cluster_cap_for(int head_size) {
   switch (head_size) {
     case 64: return cluster_cap<64>();
@@ -1217,6 +1286,31 @@ static int heads_per_cta(int num_seqs, int num_heads, int num_kv_heads, int head
   return 1;
 }
 
+// split_tokens / num_splits for a wanted factor (the tail of choose_split): splits are whole rounds of the CTA's warps
+static void choose_split_exact(int max_seq_len, int warps, int want, int* num_splits, int* split_tokens) {
+  const int quantum = 32 * warps;
+  int ns = want < 1 ? 1 : want;
+  int st = max_seq_len > 0 ? (max_seq_len + ns - 1) / ns : quantum;
+  st = (st + quantum - 1) / quantum * quantum;
+  ns = max_seq_len > 0 ? (max_seq_len + st - 1) / st : 1;
+  *num_splits = ns < 1 ? 1 : ns;
+  *split_tokens = st;
+}
+
+// Resident CTAs per SM of the default pa_v1_kernel of a head size (what shared memory allows; 3 / 3 / 2 / 2 / 2 / 1 / 1).
+static int classic_ctas_per_sm(int head_size) {
+  auto per = [](int smem) { return (227 * 1024) / (smem + 1024); };
+  switch (head_size) {
+    case 64: return per(PaCfg<64, 16, default_warps(64), 2>::SMEM);
+    case 80: return per(PaCfg<80, 16, default_warps(80), 2>::SMEM);
+    case 96: return per(PaCfg<96, 16, default_warps(96), 2>::SMEM);
+    case 112: return per(PaCfg<112, 16, default_warps(112), 2>::SMEM);
+    case 128: return per(PaCfg<128, 16, default_warps(128), 2>::SMEM);
+    case 192: return per(PaCfg<192, 16, default_warps(192), 2>::SMEM);
+    default: return per(PaCfg<256, 16, default_warps(256), 2>::SMEM);
+  }
+}
+
 // split-KV factor.  Measured on B200 (profiles/r01d_small_shapes.md): splitting costs ~2.6 us of prologue /
 // merge per extra CTA and only pays while (seq, head) pairs alone leave SMs idle, so split only when there
 // is less than one unit per SM, aim for ~2 CTAs per SM, and keep >= 256 tokens (2 stages per warp) per split.
@@ -1236,6 +1330,11 @@ static void choose_split(int num_seqs, int num_heads, int head_size, int max_seq
     ns = tuning_force_splits();
   } else if (base > 0 && base <= num_sms) {
     ns = (int)((2 * (int64_t)num_sms + base - 1) / base);
+    // ... but never more CTAs than are resident at once: the clusters of a second wave would start when the first
+    // has drained (head sizes >= 96 hold 2 or 1 CTAs per SM; 120 units x 3 splits at head size 96 were 360 CTAs on
+    // 296 slots)
+    const int by_slots = (int)((int64_t)num_sms * (variant == 0 ? classic_ctas_per_sm(head_size) : 2) / base);
+    if (ns > by_slots) ns = by_slots;
     const int max_by_len = max_seq_len / 256;
     if (ns > max_by_len) ns = max_by_len;
     if (ns > 64) ns = 64;
@@ -1342,6 +1441,17 @@ static int paged_attention_impl(void* out, const void* query, const void* key_ca
     int cap = planning ? 16 : cluster_cap_for(head_size);
     if (cap > tuning_max_cluster()) cap = tuning_max_cluster();
     choose_split(num_seqs, num_heads, head_size, max_seq_len, variant, num_sms, 1, cap, &ns, &st);
+    // every cluster of the launch must be resident at once (a second wave of clusters starts when the first has
+    // drained: 48 units x 3 splits at head size 192 took 24.9 us, x 2 splits 16.5): ask the occupancy calculator and
+    // fall back to fewer, longer splits.  (A plan query has no device and keeps the static estimate.)
+    if (!planning && variant == 0 && tuning_force_splits() == 0) {
+      const int64_t units = (int64_t)num_seqs * num_heads;
+      while (ns > 1 && max_active_clusters_for(head_size, ns) < units) {
+        const int fewer = ns - 1;
+        choose_split_exact(max_seq_len, default_warps(head_size), fewer, &ns, &st);
+        if (ns > fewer) break;   // (cannot happen: fewer splits never round up to more)
+      }
+    }
     p.cluster_merge = ns > 1;
   }
   p.num_splits = ns;
