@@ -442,6 +442,55 @@ def test_host_threads_calling_concurrently():
             assert np.array_equal(g.view(np.uint16), want.view(np.uint16)), "result differs from the single-threaded call"
 
 
+def test_first_use_inside_cuda_graph_capture():
+    """A fresh process whose FIRST call into the library happens while a CUDA graph is being captured: the once-per-
+    device set-up (function attributes, the largest cluster size, how many clusters are resident at once) must not
+    disturb the capture -- for a split launch (clusters) at a head size that holds one CTA per SM, an unsplit launch,
+    reshape_and_cache and the fused append.  The replayed graph must give the eager results."""
+    import subprocess
+    import sys
+    from vllmini_b200 import ops
+    ops.reshape_and_cache(*_tiny_reshape_args())          # this process launches something too (autouse check)
+    code = r"""
+import numpy as np, sys, torch
+sys.path.insert(0, 'tests')
+from helpers import assert_close_to_truth
+from oracle import c_oracle, paged_oracle as po
+from vllmini_b200 import _native, ops
+dev = torch.device('cuda:0')
+cases = []
+for S, H, D, B, lens in ((6, 8, 192, 16, [2048, 1500, 7, 640, 2000, 1]), (70, 12, 64, 16, None), (3, 4, 256, 32, [900, 50, 3000])):
+    lens = np.asarray(lens if lens is not None else np.random.default_rng(1).integers(1, 300, size=S), dtype=np.int32)
+    q, kc, vc, bt, sl = po.make_case(S, H, D, B, lens, seed=int(D))
+    truth = c_oracle().paged_attention_v1(q, kc, vc, D ** -0.5, bt, sl, mode='exact').astype(np.float64)
+    t = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (q, kc, vc, bt, sl)]
+    cases.append((S, H, D, B, t, torch.zeros(S, H, D, dtype=torch.float16, device=dev), truth, int(bt.shape[1]) * B))
+k_new = torch.randn(4, 12, 64, device=dev).to(torch.float16)
+kc2 = torch.zeros(8, 12, 8, 16, 8, dtype=torch.float16, device=dev)
+vc2 = torch.zeros(8, 12, 64, 16, dtype=torch.float16, device=dev)
+slots = torch.tensor([5, 17, 40, 99], dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+assert _native.launch_count() == 0                       # nothing of the library has run in this process yet
+side = torch.cuda.Stream(dev)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.stream(side):
+    with torch.cuda.graph(g, stream=side):
+        ops.reshape_and_cache(k_new, k_new, kc2, vc2, slots, 'auto', 1.0)
+        for S, H, D, B, t, out, truth, msl in cases:
+            ops.paged_attention_v1(out, t[0], t[1], t[2], H, D ** -0.5, t[3], t[4], B, msl, None, 'auto', 1.0, 0, 0, 1, 1, 0)
+for _ in range(2):
+    g.replay()
+torch.cuda.synchronize()
+for S, H, D, B, t, out, truth, msl in cases:
+    assert_close_to_truth(out.cpu().numpy(), truth, atol=1.5e-3, what=f'captured cold, D={D}')
+assert float(kc2.abs().sum()) > 0
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_small_batch_long_context_uses_split_kv():
     """S*H far below the SM count: the launcher splits the context (flash-decoding style) -- the splits of a
     (sequence, head) form a thread-block cluster and merge through distributed shared memory -- and must reproduce
