@@ -55,6 +55,27 @@ def test_plan_names_the_launched_instantiation():
         _native.plan(1, 12, 12, 72, 16, 64)
 
 
+def test_split_factor_never_exceeds_the_resident_slots():
+    """A split launch must fit the GPU at once (a second wave of clusters starts when the first has drained): the
+    factor is capped by SMs x CTAs per SM / units -- 3 CTAs per SM at head sizes 64 / 80, 2 at 96 / 112 / 128, 1 at
+    192 / 256 -- besides the 16-CTA cluster limit and the 256-token minimum per split.  (On a device the launcher
+    additionally asks cudaOccupancyMaxActiveClusters; a plan query is device-free and uses the static estimate.)"""
+    import itertools
+    slots = {64: 3, 80: 3, 96: 2, 112: 2, 128: 2, 192: 1, 256: 1}
+    for D, S, H, ctx in itertools.product(slots, (1, 2, 3, 6, 10, 16, 40, 100, 148, 149), (1, 3, 8, 12), (256, 1024, 3072, 32768)):
+        plan = _native.plan(S, H, H, D, 16, ctx)
+        gx, gy, gz = (int(x) for x in re.search(r"grid=\((\d+),(\d+),(\d+)\)", plan).groups())
+        assert (gx, gy) == (H, S) and 1 <= gz <= 16, plan
+        if gz > 1:
+            assert S * H <= 148, plan                                    # split only below one unit per SM
+            assert S * H * gz <= 148 * slots[D], (plan, "more CTAs than resident slots")
+            assert ctx // gz >= 128, plan
+    # the cases that motivated the cap (profiles/r02m_split_occupancy.md)
+    assert "grid=(3,40,2)" in _native.plan(40, 3, 3, 96, 32, 3072)
+    assert "grid=(10,10,1)" in _native.plan(10, 10, 10, 256, 16, 2048)
+    assert "grid=(8,16,2)" in _native.plan(16, 8, 8, 128, 16, 1024)
+
+
 def test_library_size_and_kernel_inventory():
     """No dead experiment ships: the product library holds the default instantiation per (head size, block size)
     [+ fused append], the grouped-query kernels, the v2 reduce kernels and the cache / driver helpers -- no
